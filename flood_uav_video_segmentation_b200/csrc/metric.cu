@@ -1,0 +1,220 @@
+// metric.cu — per-class intersection / union / target counts.
+//
+// fuvs_confusion       <- intersectionAndUnionGPU util/util.py:52-63 (torch.histc
+//                         binning) and intersectionAndUnion util/util.py:36-47
+//                         (np.histogram binning, closed last bin), as dispatched
+//                         by BaseModel.compute_metrics base/foundation.py:333-344
+// fuvs_temporal_counts <- the temporal-consistency loop flow/base.py:280-295
+//
+// Integer-only: per-thread packed 8-bit counters -> REDUX warp sums -> one
+// shared-memory merge per block -> 3K 64-bit atomics per block.  No float
+// atomics anywhere, so results are run-to-run identical.
+#include "fuvs_common.cuh"
+
+namespace fuvs {
+
+// bin index of a label value, or -1 if the histogram drops it
+__device__ __forceinline__ int bin_of(long long v, int K, int np_bins) {
+  if (np_bins) {                       // np.histogram(bins=arange(K+1)): [0,1) ... [K-1,K]
+    if (v < 0 || v > K) return -1;
+    return v == K ? K - 1 : static_cast<int>(v);
+  }
+  if (K == 1) return (v >= -1 && v <= 1) ? 0 : -1;   // histc widens min==max to [min-1, max+1]
+  if (v < 0 || v > K - 1) return -1;                  // histc(bins=K, min=0, max=K-1) ignores outliers
+  return static_cast<int>(v);
+}
+
+template <typename PT, typename TT, bool PACKED>
+__global__ void __launch_bounds__(256)
+confusion_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long long N, int K, long long ignore,
+                 int np_bins, int mutate, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned sh[PACKED ? 24 : 768];
+  Hist3Packed hist;
+  WarpTotals<8> tot;
+  hist.clear();
+  tot.clear();
+  if (!PACKED) smem_hist_clear(sh);
+  const PT ign_p = static_cast<PT>(ignore);
+  const long long per_iter = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  const long long nround = ((N + per_iter - 1) / per_iter) * per_iter;
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x * 4; base < nround; base += per_iter) {
+    PT o[4];
+    TT t[4];
+    bool live[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = base + j * blockDim.x + threadIdx.x;
+      live[j] = i < N;
+      if (live[j]) {
+        o[j] = pred[i];
+        t[j] = __ldcs(target + i);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live[j]) continue;
+      const long long tv = static_cast<long long>(t[j]);
+      PT ov = o[j];
+      if (tv == ignore) {                               // util/util.py:57 / :41
+        ov = ign_p;
+        if (mutate) pred[base + j * blockDim.x + threadIdx.x] = ign_p;
+      }
+      const long long ovl = static_cast<long long>(ov);
+      const int bo = bin_of(ovl, K, np_bins), bt = bin_of(tv, K, np_bins);
+      if (PACKED) {
+        const unsigned long long fo = bo >= 0 ? (1ull << (8 * (bo & 7))) : 0ull;
+        const unsigned long long ft = bt >= 0 ? (1ull << (8 * (bt & 7))) : 0ull;
+        hist.O += fo;
+        hist.T += ft;
+        hist.I += (ovl == tv) ? fo : 0ull;
+      } else {
+        if (bo >= 0) atomicAdd(&sh[256 + bo], 1u);
+        if (bt >= 0) atomicAdd(&sh[512 + bt], 1u);
+        if (bo >= 0 && ovl == tv) atomicAdd(&sh[bo], 1u);
+      }
+    }
+    if (PACKED) warp_accumulate<8>(hist, tot);
+  }
+  if (PACKED) {
+    // block_flush_counts<8> walks 8 bins; only the first K rows exist in counts
+    const int tid = threadIdx.x;
+    if (tid < 24) sh[tid] = 0u;
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (tot.I[c]) atomicAdd(&sh[c], tot.I[c]);
+        if (tot.O[c]) atomicAdd(&sh[8 + c], tot.O[c]);
+        if (tot.T[c]) atomicAdd(&sh[16 + c], tot.T[c]);
+      }
+    }
+    __syncthreads();
+    if (tid < K) {
+      const unsigned long long i = sh[tid], o = sh[8 + tid], t = sh[16 + tid];
+      if (i) atomicAdd(counts + tid, i);
+      if (o + t - i) atomicAdd(counts + K + tid, o + t - i);
+      if (t) atomicAdd(counts + 2 * K + tid, t);
+    }
+  } else {
+    smem_hist_flush(sh, counts, K);
+  }
+}
+
+template <int VEC, int KT>
+__global__ void __launch_bounds__(256)
+temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
+                       int K, int ignore, unsigned long long* __restrict__ counts) {
+  // KT = 8: packed path (K <= 8); KT = 0: shared-memory histogram (K <= 256)
+  __shared__ unsigned sh[KT ? 24 : 768];
+  Hist3Packed hist;
+  WarpTotals<8> tot;
+  hist.clear();
+  tot.clear();
+  if (!KT) smem_hist_clear(sh);
+  const long long nvec = HW / VEC;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long nround = (nvec + 31) & ~31ll;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nround; v += stride) {
+    if (v < nvec) {
+      const long long pix = v * VEC;
+      LVec<VEC> last;
+      bool have_last = false;
+      if (tc_prev) {
+        last.load(tc_prev + pix);
+        have_last = true;
+      }
+      for (int p = 0; p < n; ++p) {
+        LVec<VEC> lab;
+        lab.load(labels + static_cast<long long>(p) * HW + pix);
+        if (have_last) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            if (KT) hist.add(lab.v[i], last.v[i], ignore, K);
+            else smem_hist_add(sh, lab.v[i], last.v[i], ignore, K);
+          }
+        }
+        last = lab;
+        have_last = true;
+      }
+    }
+    if (KT) warp_accumulate<8>(hist, tot);
+  }
+  if (KT) block_flush_counts<8>(tot, sh, counts, K);
+  else smem_hist_flush(sh, counts, K);
+}
+
+template <typename K>
+static int persistent_grid(K kernel, long long work_items, int threads) {
+  const long long need = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * blocks_per_sm(kernel, threads);
+  long long g = need < cap ? need : cap;
+  return static_cast<int>(g > 0 ? g : 1);
+}
+
+int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
+                           int ignore_index, long long* counts, cudaStream_t st) {
+  if (!labels || !counts || n < 1 || HW < 0 || K < 1 || K > 256)
+    return set_error(FUVS_EINVAL, "temporal_counts: bad arguments n=%d HW=%lld K=%d", n, HW, K);
+  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "temporal_counts: n=%d exceeds %d", n, FUVS_MAX_FRAMES);
+  if (HW == 0 || (n == 1 && !tc_prev)) return FUVS_OK;
+  auto cu = reinterpret_cast<unsigned long long*>(counts);
+  const bool vec4 = (HW % 4 == 0) && aligned4(labels) && (!tc_prev || aligned4(tc_prev));
+  const int threads = 256;
+#define FUVS_TC(V, KT_)                                                                                 \
+  {                                                                                                     \
+    const int grid = persistent_grid(temporal_counts_kernel<V, KT_>, HW / V, threads);                  \
+    temporal_counts_kernel<V, KT_><<<grid, threads, 0, st>>>(labels, n, HW, tc_prev, K, ignore_index, cu); \
+  }
+  if (K <= 8) {
+    if (vec4) FUVS_TC(4, 8) else FUVS_TC(1, 8)
+  } else {
+    if (vec4) FUVS_TC(4, 0) else FUVS_TC(1, 0)
+  }
+#undef FUVS_TC
+  return check_launch("fuvs_temporal_counts");
+}
+
+template <typename PT, typename TT>
+static int launch_confusion(void* pred, const void* target, long long N, int K, int ignore, int flags,
+                            long long* counts, cudaStream_t st) {
+  auto cu = reinterpret_cast<unsigned long long*>(counts);
+  const int np_bins = flags & 1, mutate = (flags & FUVS_MUTATE_PRED) ? 1 : 0;
+  const int threads = 256;
+  if (K <= 8) {
+    const int grid = persistent_grid(confusion_kernel<PT, TT, true>, (N + 3) / 4, threads);
+    confusion_kernel<PT, TT, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), N,
+                                                             K, ignore, np_bins, mutate, cu);
+  } else {
+    const int grid = persistent_grid(confusion_kernel<PT, TT, false>, (N + 3) / 4, threads);
+    confusion_kernel<PT, TT, false><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target),
+                                                              N, K, ignore, np_bins, mutate, cu);
+  }
+  return check_launch("fuvs_confusion");
+}
+
+}  // namespace fuvs
+
+extern "C" int fuvs_confusion(void* pred, int pred_is_i64, const void* target, int target_is_i64, long long N, int K,
+                              int ignore_index, int flags, long long* counts, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  if (N < 0 || K < 1 || K > 256 || !counts) return set_error(FUVS_EINVAL, "confusion: bad arguments N=%lld K=%d", N, K);
+  if (N == 0) return FUVS_OK;
+  if (!pred || !target) return set_error(FUVS_EINVAL, "confusion: NULL label pointer");
+  if ((pred_is_i64 && !aligned8(pred)) || (target_is_i64 && !aligned8(target)))
+    return set_error(FUVS_EALIGN, "confusion: int64 labels must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pred_is_i64) {
+    if (target_is_i64) return launch_confusion<long long, long long>(pred, target, N, K, ignore_index, flags, counts, st);
+    return launch_confusion<long long, uint8_t>(pred, target, N, K, ignore_index, flags, counts, st);
+  }
+  if (target_is_i64) return launch_confusion<uint8_t, long long>(pred, target, N, K, ignore_index, flags, counts, st);
+  return launch_confusion<uint8_t, uint8_t>(pred, target, N, K, ignore_index, flags, counts, st);
+}
+
+extern "C" int fuvs_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
+                                    int ignore_index, long long* counts, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  return launch_temporal_counts(labels, n, HW, tc_prev, K, ignore_index, counts, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,242 @@
+// warp.cu — backward bilinear warp by a flow grid (F.grid_sample, bilinear,
+// padding_mode="border") and the fused dense-flow interval.
+//
+// fuvs_warp_step      <- FlowModel.warp, flow/model.py:244-249 (align_corners
+//                        False) and the default-grid resample flow/model.py:157
+//                        (align_corners True)
+// fuvs_dense_interval <- flow/model.py:208-239 + flow/base.py:276-277 when the
+//                        grids are dense [H,W,2]
+//
+// Dense schedule: the forward chain L_j = warp(L_{j-1}, gl_j)
+// and the backward chain R_j = warp(R_{j-1}, gr_j) advance in lock step, one
+// launch per step.  Frame p = w0*L_p + w1*R_{n-p} is finished in the step
+// max(p, n-p): the state produced in that step is still in registers, the
+// other one is re-read pointwise.  States n-1 are never written; frame 0
+// (arg-max of the key frame) rides on step 1.
+#include "fuvs_common.cuh"
+
+namespace fuvs {
+
+int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
+                           int ignore_index, long long* counts, cudaStream_t st);
+int launch_argmax(const float* logits, int frames, int C, long long HW, uint8_t* u8, long long* i64, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// generic step: dst[c, y, x] = bilinear(src[c], grid[y, x])
+// ---------------------------------------------------------------------------
+struct WarpProblem {
+  const float* src;
+  const float* grid;
+  float* dst;
+};
+
+template <class NM>
+__global__ void __launch_bounds__(256)
+warp_step_kernel(WarpProblem p0, WarpProblem p1, int C, int Hin, int Win, int Hg, int Wg, int align_corners,
+                 int cchunk, int nchunks) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= Wg || y >= Hg) return;
+  const int side = blockIdx.z / nchunks;
+  const int chunk = blockIdx.z - side * nchunks;
+  const WarpProblem P = side ? p1 : p0;
+  const long long opix = static_cast<long long>(y) * Wg + x;
+  const float2 g = __ldg(reinterpret_cast<const float2*>(P.grid) + opix);
+  const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, align_corners != 0);
+  const long long in_plane = static_cast<long long>(Hin) * Win;
+  const long long out_plane = static_cast<long long>(Hg) * Wg;
+  const int c0 = chunk * cchunk;
+  const int c1 = min(C, c0 + cchunk);
+#pragma unroll 4
+  for (int c = c0; c < c1; ++c) {
+    P.dst[c * out_plane + opix] = gs_fetch<NM>(P.src + c * in_plane, t, Win);
+  }
+}
+
+template <class NM>
+static int launch_warp_step(const float* src0, const float* grid0, float* dst0, const float* src1, const float* grid1,
+                            float* dst1, int C, int Hin, int Win, int Hg, int Wg, int align_corners, cudaStream_t st) {
+  const int sides = src1 ? 2 : 1;
+  const int bx = (Wg + 31) / 32, by = (Hg + 7) / 8;
+  // split the channel loop so that small grids with many channels (feature
+  // maps: C=2048 at 67x120) still fill the 148 SMs a few times over
+  const long long spatial_blocks = static_cast<long long>(bx) * by * sides;
+  const long long want = 4ll * sm_count();
+  int nchunks = 1;
+  if (spatial_blocks < want) nchunks = static_cast<int>((want + spatial_blocks - 1) / spatial_blocks);
+  if (nchunks > C) nchunks = C;
+  int cchunk = (C + nchunks - 1) / nchunks;
+  nchunks = (C + cchunk - 1) / cchunk;
+  if (static_cast<long long>(sides) * nchunks > 65535 || by > 65535)
+    return set_error(FUVS_EINVAL, "warp_step: grid too large (Hg=%d, C=%d)", Hg, C);
+  dim3 grid(bx, by, sides * nchunks), block(32, 8);
+  WarpProblem p0{src0, grid0, dst0}, p1{src1, grid1, dst1};
+  warp_step_kernel<NM><<<grid, block, 0, st>>>(p0, p1, C, Hin, Win, Hg, Wg, align_corners, cchunk, nchunks);
+  return check_launch("fuvs_warp_step");
+}
+
+// ---------------------------------------------------------------------------
+// dense lock-step kernel
+// ---------------------------------------------------------------------------
+struct DenseStep {
+  const float* srcL; const float* srcR;      // states j-1, [C,H,W]
+  const float* gridL; const float* gridR;    // [H,W,2]
+  float* dstL; float* dstR;                  // states j or NULL (last step)
+  // frame A = frame j      : wA0 * L_j(reg)   + wA1 * R_{n-j} (pointR, or this step's R if NULL)
+  // frame B = frame n-j    : wB0 * L_{n-j}(pointL) + wB1 * R_j(reg)
+  int emitA, emitB;
+  const float* pointR; const float* pointL;
+  float wA0, wA1, wB0, wB1;
+  uint8_t* labelA; uint8_t* labelB;
+  float* logitA; float* logitB;
+  // frame 0 on step 1
+  const float* key0; uint8_t* label0; float* logit0;
+};
+
+template <class NM, int CT>
+__global__ void __launch_bounds__(256)
+dense_step_kernel(const DenseStep A, int Crt, int H, int W) {
+  const int C = CT > 0 ? CT : Crt;
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const long long HW = static_cast<long long>(H) * W;
+  const long long pix = static_cast<long long>(y) * W + x;
+  const float2 gl = __ldg(reinterpret_cast<const float2*>(A.gridL) + pix);
+  const float2 gr = __ldg(reinterpret_cast<const float2*>(A.gridR) + pix);
+  const GsTap tl = gs_setup<NM>(gl.x, gl.y, H, W, false);
+  const GsTap tr = gs_setup<NM>(gr.x, gr.y, H, W, false);
+  ArgMax amA, amB, am0;
+  amA.init(0.f); amB.init(0.f); am0.init(0.f);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const long long o = c * HW + pix;
+    const float Lc = gs_fetch<NM>(A.srcL + c * HW, tl, W);
+    const float Rc = gs_fetch<NM>(A.srcR + c * HW, tr, W);
+    if (A.dstL) A.dstL[o] = Lc;
+    if (A.dstR) A.dstR[o] = Rc;
+    if (A.emitA) {
+      const float r = A.pointR ? __ldg(A.pointR + o) : Rc;
+      const float v = blend2(A.wA0, Lc, A.wA1, r);
+      if (c == 0) amA.init(v); else amA.push(v, c);
+      if (A.logitA) __stcs(A.logitA + o, v);
+    }
+    if (A.emitB) {
+      const float l = __ldg(A.pointL + o);
+      const float v = blend2(A.wB0, l, A.wB1, Rc);
+      if (c == 0) amB.init(v); else amB.push(v, c);
+      if (A.logitB) __stcs(A.logitB + o, v);
+    }
+    if (A.key0) {
+      const float v = __ldg(A.key0 + o);
+      if (c == 0) am0.init(v); else am0.push(v, c);
+      if (A.logit0) __stcs(A.logit0 + o, v);
+    }
+  }
+  if (A.emitA && A.labelA) A.labelA[pix] = static_cast<uint8_t>(amA.idx);
+  if (A.emitB && A.labelB) A.labelB[pix] = static_cast<uint8_t>(amB.idx);
+  if (A.key0 && A.label0) A.label0[pix] = static_cast<uint8_t>(am0.idx);
+}
+
+template <class NM>
+static int launch_dense_step(const DenseStep& a, int C, int H, int W, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+  if (grid.y > 65535) return set_error(FUVS_EINVAL, "dense: H=%d too large", H);
+  switch (C) {
+    case 2: dense_step_kernel<NM, 2><<<grid, block, 0, st>>>(a, C, H, W); break;
+    case 5: dense_step_kernel<NM, 5><<<grid, block, 0, st>>>(a, C, H, W); break;
+    default: dense_step_kernel<NM, 0><<<grid, block, 0, st>>>(a, C, H, W); break;
+  }
+  return check_launch("fuvs_dense_interval(step)");
+}
+
+}  // namespace fuvs
+
+extern "C" int fuvs_warp_step(const float* src0, const float* grid0, float* dst0, const float* src1,
+                              const float* grid1, float* dst1, int C, int Hin, int Win, int Hg, int Wg,
+                              int align_corners, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  if (!src0 || !grid0 || !dst0 || C < 1 || Hin < 1 || Win < 1 || Hg < 0 || Wg < 0)
+    return set_error(FUVS_EINVAL, "warp_step: bad arguments C=%d in=%dx%d grid=%dx%d", C, Hin, Win, Hg, Wg);
+  if ((src1 != nullptr) != (grid1 != nullptr) || (src1 != nullptr) != (dst1 != nullptr))
+    return set_error(FUVS_EINVAL, "warp_step: second problem must be all-NULL or all-set");
+  if (static_cast<long long>(Hin) * Win >= (1ll << 31))
+    return set_error(FUVS_EINVAL, "warp_step: source plane exceeds 2^31 elements");
+  if (!aligned8(grid0) || (grid1 && !aligned8(grid1))) return set_error(FUVS_EALIGN, "warp_step: grids must be 8-byte aligned");
+  if (Hg == 0 || Wg == 0) return FUVS_OK;
+  return launch_warp_step<Nm>(src0, grid0, dst0, src1, grid1, dst1, C, Hin, Win, Hg, Wg, align_corners,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" long long fuvs_dense_scratch_floats(int C, int H, int W, int n) {
+  if (n <= 2) return 0;
+  return 2ll * (n - 2) * C * static_cast<long long>(H) * W;
+}
+
+extern "C" int fuvs_dense_interval(const float* prev, const float* next, const float* grids_left,
+                                   const float* grids_right, int C, int H, int W, int n, float* scratch,
+                                   uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
+                                   int ignore_index, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  if (!prev || C < 1 || H < 1 || W < 1 || n < 1) return set_error(FUVS_EINVAL, "dense: bad shape C=%d H=%d W=%d n=%d", C, H, W, n);
+  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "dense: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!next || !grids_left || !grids_right)) return set_error(FUVS_EINVAL, "dense: next/grids are NULL but n=%d", n);
+  if (n > 2 && !scratch) return set_error(FUVS_EINVAL, "dense: scratch is NULL (need %lld floats)", fuvs_dense_scratch_floats(C, H, W, n));
+  if ((labels || counts) && C > 256) return set_error(FUVS_EINVAL, "dense: uint8 label maps need C <= 256 (C=%d)", C);
+  if (counts && !labels) return set_error(FUVS_EINVAL, "dense: counts need the label maps (labels is NULL)");
+  const long long HW = static_cast<long long>(H) * W;
+  if (HW >= (1ll << 31)) return set_error(FUVS_EINVAL, "dense: plane exceeds 2^31 elements");
+  if (n > 1 && (!aligned8(grids_left) || !aligned8(grids_right))) return set_error(FUVS_EALIGN, "dense: grids must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long S = static_cast<long long>(C) * HW;
+
+  if (n == 1) {
+    if (labels) {
+      if (int e = launch_argmax(prev, 1, C, HW, labels, nullptr, st)) return e;
+    }
+    if (logits) {
+      if (cudaMemcpyAsync(logits, prev, S * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return set_error(FUVS_ECUDA, "dense: logits copy failed");
+    }
+  } else {
+    BlendWeights w;
+    make_blend_weights(n, &w);
+    float* Lst = scratch;                       // states 1..n-2
+    float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
+    for (int j = 1; j <= n - 1; ++j) {
+      DenseStep a{};
+      a.srcL = (j == 1) ? prev : Lst + (j - 2) * S;
+      a.srcR = (j == 1) ? next : Rst + (j - 2) * S;
+      a.gridL = grids_left + static_cast<long long>(j - 1) * HW * 2;
+      a.gridR = grids_right + static_cast<long long>(j - 1) * HW * 2;
+      a.dstL = (j <= n - 2) ? Lst + (j - 1) * S : nullptr;
+      a.dstR = (j <= n - 2) ? Rst + (j - 1) * S : nullptr;
+      const bool want_out = labels || logits;
+      if (want_out && 2 * j >= n) {
+        const int pA = j, pB = n - j;
+        a.emitA = 1;
+        a.pointR = (pB == j) ? nullptr : Rst + (pB - 1) * S;   // R_{n-pA}
+        a.wA0 = w.w0[pA]; a.wA1 = w.w1[pA];
+        a.labelA = labels ? labels + pA * HW : nullptr;
+        a.logitA = logits ? logits + pA * S : nullptr;
+        if (pB != pA) {
+          a.emitB = 1;
+          a.pointL = Lst + (pB - 1) * S;                         // L_{pB}
+          a.wB0 = w.w0[pB]; a.wB1 = w.w1[pB];
+          a.labelB = labels ? labels + pB * HW : nullptr;
+          a.logitB = logits ? logits + pB * S : nullptr;
+        }
+      }
+      if (j == 1 && want_out) {
+        a.key0 = prev;
+        a.label0 = labels;
+        a.logit0 = logits;
+      }
+      if (int e = launch_dense_step<Nm>(a, C, H, W, st)) return e;
+    }
+  }
+  if (counts) return launch_temporal_counts(labels, n, HW, tc_prev, C, ignore_index, counts, st);
+  return FUVS_OK;
+}

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C ABI (include/fuvs.h).
+
+Each function validates shapes/dtypes, allocates outputs with torch (device
+memory plumbing only), passes raw pointers + the current CUDA stream to
+libfuvs.so and returns tensors.  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import FuvsError, check, load, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise FuvsError(f"{what}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def new_counts(K: int, device) -> torch.Tensor:
+    """Device-resident int64 [3,K] accumulator: rows (intersection, union, target)."""
+    return torch.zeros((3, K), dtype=torch.int64, device=device)
+
+
+def _stack_grids(mvs, what: str) -> torch.Tensor:
+    """python list of k-1 grids [1,Hg,Wg,2] (or [Hg,Wg,2]) -> fp32 [k-1,Hg,Wg,2].
+
+    FlowModel.warp casts grids with .float() (flow/model.py:246-247)."""
+    if isinstance(mvs, torch.Tensor):
+        g = mvs
+    else:
+        g = torch.stack([m.reshape(m.shape[-3], m.shape[-2], 2) for m in mvs], 0)
+    if g.dtype != torch.float32:
+        g = g.float()
+    return g.contiguous()
+
+
+def linear_blend_argmax(prev, nxt, n, *, want_labels=True, want_logits=False, tc_prev=None, counts=None,
+                        ignore_index=255):
+    """fuvs_linear_blend_argmax.  prev/nxt: [C,H,W] or [1,C,H,W]."""
+    dev = require_cuda(prev, nxt, tc_prev, counts, what="linear_blend_argmax")
+    prev = _f32c(prev, "prev")
+    C, H, W = prev.shape[-3:]
+    if n > 1:
+        nxt = _f32c(nxt, "next")
+        if nxt.shape[-3:] != prev.shape[-3:]:
+            raise FuvsError(f"linear_blend_argmax: key frames differ in shape {tuple(prev.shape)} vs {tuple(nxt.shape)}")
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_labels else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_linear_blend_argmax(ptr(prev), ptr(nxt) if n > 1 else None, C, H, W, n, ptr(labels),
+                                              ptr(logits), ptr(tc_prev), ptr(counts), ignore_index, stream_ptr(dev)))
+    return labels, logits
+
+
+def _check_tc(tc_prev, counts, H, W, K):
+    if tc_prev is not None:
+        if tc_prev.dtype != torch.uint8 or tuple(tc_prev.shape[-2:]) != (H, W) or not tc_prev.is_contiguous():
+            raise FuvsError("tc_prev must be a contiguous uint8 [H,W] label map")
+    if counts is not None:
+        if counts.dtype != torch.int64 or tuple(counts.shape) != (3, K) or not counts.is_contiguous():
+            raise FuvsError(f"counts must be a contiguous int64 [3,{K}] tensor")
+
+
+def warp_step(src0, grid0, src1=None, grid1=None, *, align_corners=False):
+    """fuvs_warp_step: F.grid_sample(bilinear, border) of one or two [C,Hin,Win] maps."""
+    dev = require_cuda(src0, grid0, src1, grid1, what="warp_step")
+    src0 = _f32c(src0, "src0")
+    grid0 = _f32c(grid0 if grid0.dtype == torch.float32 else grid0.float(), "grid0")
+    C, Hin, Win = src0.shape[-3:]
+    Hg, Wg = grid0.shape[-3:-1]
+    dst0 = torch.empty((C, Hg, Wg), dtype=torch.float32, device=dev)
+    dst1 = None
+    if src1 is not None:
+        src1 = _f32c(src1, "src1")
+        grid1 = _f32c(grid1 if grid1.dtype == torch.float32 else grid1.float(), "grid1")
+        if src1.shape[-3:] != src0.shape[-3:] or grid1.shape[-3:] != grid0.shape[-3:]:
+            raise FuvsError("warp_step: the two problems must have the same shapes")
+        dst1 = torch.empty_like(dst0)
+    with torch.cuda.device(dev):
+        check(load().fuvs_warp_step(ptr(src0), ptr(grid0), ptr(dst0), ptr(src1), ptr(grid1), ptr(dst1), C, Hin, Win,
+                                    Hg, Wg, 1 if align_corners else 0, stream_ptr(dev)))
+    return dst0, dst1
+
+
+def dense_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, want_logits=False, tc_prev=None,
+                   counts=None, ignore_index=255, scratch=None):
+    """fuvs_dense_interval.  grids_*: list of n-1 [1,H,W,2] tensors or a stacked [n-1,H,W,2]."""
+    dev = require_cuda(prev, nxt, tc_prev, counts, what="dense_interval")
+    prev = _f32c(prev, "prev")
+    C, H, W = prev.shape[-3:]
+    gl = gr = None
+    if n > 1:
+        nxt = _f32c(nxt, "next")
+        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
+        require_cuda(gl, gr, what="dense_interval(grids)")
+        if tuple(gl.shape) != (n - 1, H, W, 2) or tuple(gr.shape) != (n - 1, H, W, 2):
+            raise FuvsError(f"dense_interval: grids must be [{n - 1},{H},{W},2], got {tuple(gl.shape)} / {tuple(gr.shape)}")
+    need = int(load().fuvs_dense_scratch_floats(C, H, W, n))
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_dense_interval(ptr(prev), ptr(nxt) if n > 1 else None, ptr(gl), ptr(gr), C, H, W, n,
+                                         ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
+                                         ignore_index, stream_ptr(dev)))
+    return labels, logits
+
+
+def block_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, want_logits=False, tc_prev=None,
+                   counts=None, ignore_index=255, scratch=None):
+    """fuvs_block_interval.  grids_*: list of n-1 [1,Hg,Wg,2] tensors or stacked [n-1,Hg,Wg,2]."""
+    dev = require_cuda(prev, nxt, tc_prev, counts, what="block_interval")
+    prev = _f32c(prev, "prev")
+    C, H, W = prev.shape[-3:]
+    gl = gr = None
+    Hg = Wg = 0
+    if n > 1:
+        nxt = _f32c(nxt, "next")
+        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
+        require_cuda(gl, gr, what="block_interval(grids)")
+        Hg, Wg = gl.shape[1:3]
+        if tuple(gl.shape) != (n - 1, Hg, Wg, 2) or tuple(gr.shape) != tuple(gl.shape):
+            raise FuvsError(f"block_interval: grids must both be [{n - 1},Hg,Wg,2], got {tuple(gl.shape)} / {tuple(gr.shape)}")
+    need = int(load().fuvs_block_scratch_floats(C, Hg, Wg, n))
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_block_interval(ptr(prev), ptr(nxt) if n > 1 else None, ptr(gl), ptr(gr), C, H, W, Hg, Wg, n,
+                                         ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
+                                         ignore_index, stream_ptr(dev)))
+    return labels, logits
+
+
+def upsample_bilinear_ac(src, size, out=None):
+    """fuvs_upsample_bilinear_ac: F.interpolate(src, size, mode='bilinear', align_corners=True) for [...,Hin,Win]."""
+    dev = require_cuda(src, out, what="upsample_bilinear_ac")
+    src = _f32c(src, "src")
+    Hin, Win = src.shape[-2:]
+    Hout, Wout = int(size[0]), int(size[1])
+    lead = tuple(src.shape[:-2])
+    planes = 1
+    for s in lead:
+        planes *= s
+    if out is None:
+        out = torch.empty(lead + (Hout, Wout), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != lead + (Hout, Wout) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise FuvsError("upsample_bilinear_ac: bad `out` tensor")
+    with torch.cuda.device(dev):
+        check(load().fuvs_upsample_bilinear_ac(ptr(src), ptr(out), planes, Hin, Win, Hout, Wout, stream_ptr(dev)))
+    return out
+
+
+def blend_argmax(a, b, wa, wb, *, want_out=True, want_labels=False, out=None):
+    """fuvs_blend_argmax on [F,C,H,W] (or [C,H,W]): out = fl(fl(wa*a)+fl(wb*b)), labels = argmax_C."""
+    dev = require_cuda(a, b, out, what="blend_argmax")
+    a = _f32c(a, "a")
+    if b is not None:
+        b = _f32c(b, "b")
+        if b.shape != a.shape:
+            raise FuvsError(f"blend_argmax: shapes differ {tuple(a.shape)} vs {tuple(b.shape)}")
+    if a.dim() == 3:
+        frames, (Cc, H, W) = 1, a.shape
+    elif a.dim() == 4:
+        frames, Cc, H, W = a.shape
+    else:
+        raise FuvsError("blend_argmax: expected [C,H,W] or [F,C,H,W]")
+    if want_out and out is None:
+        out = torch.empty_like(a)
+    if out is not None and (out.shape != a.shape or out.dtype != torch.float32 or not out.is_contiguous()):
+        raise FuvsError("blend_argmax: bad `out` tensor")
+    labels = torch.empty((frames, H, W), dtype=torch.uint8, device=dev) if want_labels else None
+    with torch.cuda.device(dev):
+        check(load().fuvs_blend_argmax(ptr(a), ptr(b), float(wa), float(wb), frames, Cc, H * W, ptr(out), ptr(labels),
+                                       stream_ptr(dev)))
+    return out, labels
+
+
+def argmax(logits, *, dtype=torch.uint8):
+    """fuvs_argmax: logits [F,C,H,W] -> labels [F,H,W] (uint8 or int64), torch.max(dim=1)[1] semantics."""
+    dev = require_cuda(logits, what="argmax")
+    logits = _f32c(logits, "logits")
+    if logits.dim() != 4:
+        raise FuvsError("argmax: expected [F,C,H,W]")
+    F_, Cc, H, W = logits.shape
+    if dtype == torch.uint8:
+        u8, i64 = torch.empty((F_, H, W), dtype=torch.uint8, device=dev), None
+    elif dtype == torch.int64:
+        u8, i64 = None, torch.empty((F_, H, W), dtype=torch.int64, device=dev)
+    else:
+        raise FuvsError("argmax: dtype must be torch.uint8 or torch.int64")
+    with torch.cuda.device(dev):
+        check(load().fuvs_argmax(ptr(logits), F_, Cc, H * W, ptr(u8), ptr(i64), stream_ptr(dev)))
+    return u8 if u8 is not None else i64
+
+
+def confusion(pred, target, K, ignore_index=255, *, counts=None, numpy_bins=False, mutate_pred=False):
+    """fuvs_confusion: accumulates (I,U,T) of util/util.py:52-63 (or :36-47 with numpy_bins) into counts [3,K]."""
+    dev = require_cuda(pred, target, counts, what="confusion")
+    if pred.shape != target.shape:
+        raise FuvsError(f"confusion: shapes differ {tuple(pred.shape)} vs {tuple(target.shape)}")
+    for t, name in ((pred, "pred"), (target, "target")):
+        if t.dtype not in (torch.uint8, torch.int64):
+            raise FuvsError(f"confusion: {name} must be uint8 or int64, got {t.dtype}")
+    if not pred.is_contiguous():
+        if mutate_pred:
+            raise FuvsError("confusion: mutate_pred needs a contiguous pred")
+        pred = pred.contiguous()
+    target = target.contiguous()
+    if counts is None:
+        counts = new_counts(K, dev)
+    _check_tc(None, counts, 0, 0, K)
+    flags = (_lib.FUVS_BINS_NPHIST if numpy_bins else _lib.FUVS_BINS_HISTC) | (_lib.FUVS_MUTATE_PRED if mutate_pred else 0)
+    with torch.cuda.device(dev):
+        check(load().fuvs_confusion(ptr(pred), 1 if pred.dtype == torch.int64 else 0, ptr(target),
+                                    1 if target.dtype == torch.int64 else 0, pred.numel(), K, int(ignore_index), flags,
+                                    ptr(counts), stream_ptr(dev)))
+    return counts
+
+
+def temporal_counts(labels, K, ignore_index=255, *, tc_prev=None, counts=None):
+    """fuvs_temporal_counts over uint8 labels [n,H,W] (flow/base.py:280-295)."""
+    dev = require_cuda(labels, tc_prev, counts, what="temporal_counts")
+    if labels.dtype != torch.uint8 or labels.dim() != 3 or not labels.is_contiguous():
+        raise FuvsError("temporal_counts: labels must be contiguous uint8 [n,H,W]")
+    n, H, W = labels.shape
+    if counts is None:
+        counts = new_counts(K, dev)
+    _check_tc(tc_prev, counts, H, W, K)
+    with torch.cuda.device(dev):
+        check(load().fuvs_temporal_counts(ptr(labels), n, H * W, ptr(tc_prev), K, int(ignore_index), ptr(counts),
+                                          stream_ptr(dev)))
+    return counts

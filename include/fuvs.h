@@ -1,0 +1,206 @@
+/*
+ * fuvs.h — C ABI of libfuvs.so: the B200 (sm_100a) implementation of the
+ * inter-frame segmentation interpolation path of
+ * lenke182/flood-uav-video-segmentation.
+ *
+ * The reference has no FFI of its own: the seam is Python-method level
+ * (SURVEY.md §8b).  Each entry point below names the reference call site(s)
+ * it replaces, relative to the reference repository root.  The Python host
+ * layer (flood_uav_video_segmentation_b200/) binds these with ctypes; a
+ * maintainer's binding stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every pointer is DEVICE memory unless the
+ *    name ends in `_host`.  All float tensors are fp32, contiguous NCHW.
+ *    Label maps are uint8 [n,H,W].  Count buffers are int64 [3,K] laid out as
+ *    rows (area_intersection, area_union, area_target) and are ACCUMULATED
+ *    in place (the caller zeroes them at epoch start).
+ *  - The library allocates nothing persistent, borrows inputs for the
+ *    duration of the enqueue and never synchronises the device: every call
+ *    only enqueues kernels on `stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 on success, a negative FUVS_E* code otherwise (never
+ *    throws).  fuvs_last_error() returns a thread-local message for the last
+ *    failure.  Asynchronous CUDA faults surface at the caller's next sync.
+ *  - Arithmetic: every fp32 rounding step of the eager ATen op sequence the
+ *    reference issues (grid_sampler_2d, upsample_bilinear2d, mul, add) is
+ *    reproduced, so label maps and counts are bit-identical to the reference
+ *    run on torch-CUDA (see DESIGN.md "Numerics").
+ *  - No CPU fallback and no multi-backend dispatch: on a machine without an
+ *    sm_100 device every compute entry returns FUVS_ENODEV.
+ */
+#ifndef FUVS_H_
+#define FUVS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUVS_ABI_VERSION 1
+
+/* error codes */
+#define FUVS_OK        0
+#define FUVS_EINVAL   -1   /* bad shape / null pointer / unsupported size   */
+#define FUVS_EALIGN   -2   /* pointer not aligned as documented             */
+#define FUVS_ECUDA    -3   /* a CUDA runtime call failed (see last_error)   */
+#define FUVS_ENODEV   -4   /* no CUDA device / not an sm_100 device         */
+
+/* histogram conventions for fuvs_confusion (flags bit 0) */
+#define FUVS_BINS_HISTC      0  /* torch.histc(bins=K,min=0,max=K-1): util/util.py:59-61 */
+#define FUVS_BINS_NPHIST     1  /* np.histogram(bins=arange(K+1)), closed last bin: util/util.py:43-45 */
+/* flags bit 1: write the ignore substitution back into `pred`
+ * (intersectionAndUnionGPU mutates its caller's tensor, util/util.py:57) */
+#define FUVS_MUTATE_PRED     2
+
+#if defined(__GNUC__)
+#define FUVS_API __attribute__((visibility("default")))
+#else
+#define FUVS_API
+#endif
+
+typedef void* fuvs_stream_t;   /* cudaStream_t */
+
+FUVS_API int         fuvs_abi_version(void);
+FUVS_API const char* fuvs_last_error(void);
+/* Number of kernels this library has launched in the calling process. */
+FUVS_API long long   fuvs_launch_count(void);
+/* 0 if the current device can run the kernels (compute capability 10.x). */
+FUVS_API int         fuvs_device_ok(void);
+
+/* ---------------------------------------------------------------------------
+ * Linear temporal blending (model.no_warp=True, model.feature_based=False).
+ * Replaces, for one interval: flow/model.py:231-239 (fusion + cat) with
+ * warp()==identity (flow/model.py:244-249), flow/base.py:276 (max(1)[1]),
+ * flow/base.py:277 (uint8 cast) and the temporal-consistency metric loop
+ * flow/base.py:280-295 + util/util.py:52-63.
+ *
+ *   prev,next : [C,H,W] key-frame logit maps
+ *   n         : frames in the interval (= data.frame_delta); frame 0 is the
+ *               unblended key frame, frame p = fl(fl(w0p*prev)+fl(w1p*next))
+ *               with w0p=(float)((double)(n-p)/n), w1p=(float)((double)p/n)
+ *   labels    : [n,H,W] uint8 out (arg-max over C; first max wins ties, NaN
+ *               beats every number), or NULL
+ *   logits    : [n,C,H,W] fp32 out, or NULL (FlowModel.predict()'s "pred")
+ *   tc_prev   : [H,W] uint8 last label map of the previous interval
+ *               (FlowBaseModel.last_output) or NULL for the first interval
+ *   counts    : [3,K=C] int64 accumulate, or NULL: temporal-consistency
+ *               (I,U,T) of label p against label p-1 (p=0 against tc_prev)
+ *   ignore_index : as model.ignore_index (255)
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_linear_blend_argmax(const float* prev, const float* next,
+                             int C, int H, int W, int n,
+                             uint8_t* labels, float* logits,
+                             const uint8_t* tc_prev, long long* counts,
+                             int ignore_index, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * One backward-warp step: F.grid_sample(src, grid, mode="bilinear",
+ * padding_mode="border", align_corners=False|True) — flow/model.py:248
+ * (align_corners=0) and flow/model.py:157 (align_corners=1).
+ * Up to two independent (src,grid,dst) problems of the same shape are warped
+ * in one launch (the forward and the backward chain advance in lock step).
+ *
+ *   src*  : [C,Hin,Win]   grid* : [Hg,Wg,2] (x,y) normalised   dst* : [C,Hg,Wg]
+ *   src1/grid1/dst1 may all be NULL for a single-sided step.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_warp_step(const float* src0, const float* grid0, float* dst0,
+                   const float* src1, const float* grid1, float* dst1,
+                   int C, int Hin, int Win, int Hg, int Wg, int align_corners,
+                   fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Dense-flow interval (grids are [H,W,2]; the up-sample of flow/model.py:
+ * 217-218,227-228 is skipped because shapes already match).  Replaces
+ * flow/model.py:208-239 + flow/base.py:276-277 for one interval.
+ *
+ *   prev,next   : [C,H,W]
+ *   grids_left  : [n-1,H,W,2]  mvs_left[0..n-2] stacked
+ *   grids_right : [n-1,H,W,2]  mvs_right[0..n-2] stacked
+ *   scratch     : fp32 workspace of fuvs_dense_scratch_floats(C,H,W,n) floats
+ *                 (chain states 1..n-2 of both sides)
+ *   labels      : [n,H,W] uint8 out or NULL;  logits : [n,C,H,W] out or NULL
+ *   tc_prev/counts/ignore_index : as in fuvs_linear_blend_argmax
+ * ------------------------------------------------------------------------- */
+FUVS_API long long fuvs_dense_scratch_floats(int C, int H, int W, int n);
+FUVS_API int fuvs_dense_interval(const float* prev, const float* next,
+                        const float* grids_left, const float* grids_right,
+                        int C, int H, int W, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Macro-block-grid interval (reference-faithful: grids are [Hg,Wg,2] with
+ * Hg=H/16, Wg=W/16).  The chains run at grid resolution (flow/model.py:
+ * 214-215,224-225), each state is bilinearly up-sampled to (H,W) with
+ * align_corners=True (flow/model.py:217-218,227-228), blended
+ * (flow/model.py:233-237) and arg-maxed (flow/base.py:276).
+ *
+ *   grids_left/right : [n-1,Hg,Wg,2]
+ *   scratch          : fuvs_block_scratch_floats(C,Hg,Wg,n) floats
+ * ------------------------------------------------------------------------- */
+FUVS_API long long fuvs_block_scratch_floats(int C, int Hg, int Wg, int n);
+FUVS_API int fuvs_block_interval(const float* prev, const float* next,
+                        const float* grids_left, const float* grids_right,
+                        int C, int H, int W, int Hg, int Wg, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * F.interpolate(src, size=(Hout,Wout), mode="bilinear", align_corners=True)
+ * — flow/model.py:42,68,86,103,139,150,159,179,193,206,218,228 and
+ * flow/base.py:219,232,275.   src [N*C,Hin,Win] -> dst [N*C,Hout,Wout].
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_upsample_bilinear_ac(const float* src, float* dst, long long planes,
+                              int Hin, int Win, int Hout, int Wout,
+                              fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * out = fl(fl(wa*a) + fl(wb*b)) over `planes` [H*W] planes, optional arg-max
+ * over the C planes of each of the `frames` images (planes = frames*C).
+ * Replaces flow/model.py:104 (x * ((n-index)/n)) + flow/model.py:64,84 (sum
+ * of the two sides) and flow/model.py:168,170,234-236 for one frame.
+ * wa/wb are the python doubles; the library rounds them to fp32 as ATen does.
+ * b may be NULL (out = fl(wa*a)).  out and labels may each be NULL.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_blend_argmax(const float* a, const float* b, double wa, double wb,
+                      int frames, int C, long long HW,
+                      float* out, uint8_t* labels, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * labels = logits.max(1)[1]   — flow/base.py:147,167,276.
+ *   logits [frames,C,HW] fp32 -> labels_u8 [frames,HW] and/or labels_i64.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_argmax(const float* logits, int frames, int C, long long HW,
+                uint8_t* labels_u8, long long* labels_i64,
+                fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * intersectionAndUnionGPU / intersectionAndUnion — util/util.py:52-63, 36-47.
+ *   pred   : [N] labels, uint8 (pred_is_i64=0) or int64 (pred_is_i64=1)
+ *   target : [N] labels, uint8 (target_is_i64=0) or int64 (target_is_i64=1)
+ *   counts : [3,K] int64 accumulate (I,U,T)
+ *   flags  : FUVS_BINS_HISTC | FUVS_BINS_NPHIST, optionally | FUVS_MUTATE_PRED
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_confusion(void* pred, int pred_is_i64,
+                   const void* target, int target_is_i64,
+                   long long N, int K, int ignore_index, int flags,
+                   long long* counts, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Temporal-consistency metric over finished label maps — flow/base.py:280-295:
+ * for p in 0..n-1: metric(output=labels[p], target=labels[p-1]) with p=0
+ * compared against tc_prev when it is not NULL (skipped otherwise).
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_temporal_counts(const uint8_t* labels, int n, long long HW,
+                         const uint8_t* tc_prev, int K, int ignore_index,
+                         long long* counts, fuvs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUVS_H_ */
