@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py — interpolated frames/s at 1080p (k=5) on N B200s + HBM roofline of the fused interval kernels.
+
+Contract (task prompt §④ + base contract):
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode dense|block|linear]
+  N>1 is launched by torchrun, one rank per GPU; rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json configs[1]): flow-warped logit interpolation (no_warp=False) on synthetic 1080x1920
+clips, C=5, k=5, dense [H,W,2] flow grids.  A step = `--clips-per-step` 16-frame clips = 3 intervals each = 12
+interpolated frames per clip.  `value`: inputs resident in HBM.  `e2e`: the same work through
+FlowBaseModel.predict_step with HOST (pinned) inputs, H2D and D2H inside the timed region.
+`--impl reference`: the oracle's restatement of the reference call sequence on torch-CPU (the reference is pure
+Python/torch; it cannot travel to the GPU box), one interval per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, H, W, K_DELTA, CLIP_FRAMES = 5, 1080, 1920, 5, 16
+METRIC = "interpolated_frames_per_sec_1080p_k5"
+S_BYTES = C * H * W * 4
+LB_BYTES = H * W
+
+
+def algorithmic_bytes(mode, k=K_DELTA):
+    """algorithmic HBM bytes per interval (uint8 labels)."""
+    if mode == "linear":
+        return 2 * S_BYTES + k * LB_BYTES + LB_BYTES
+    if mode == "block":
+        hg, wg = H // 16, W // 16
+        return S_BYTES + 8 * C * hg * wg * 4 + 2 * (k - 1) * hg * wg * 8 + (k + 1) * LB_BYTES
+    g = H * W * 8
+    return (5 * k - (8 if k % 2 == 0 else 7)) * S_BYTES + 2 * (k - 1) * g + (k + 1) * LB_BYTES
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- synthetic clips
+def make_grids(n_grids, mode, device, gen):
+    from flood_uav_video_segmentation_b200.synthetic import identity_grid
+    base = identity_grid(H, W, mode).to(device)
+    jit = (torch.rand((n_grids,) + tuple(base.shape), device=device, generator=gen) - 0.5) * 0.05
+    return (base.unsqueeze(0) + jit).contiguous()
+
+
+def make_clip(mode, device, seed):
+    """One 16-frame clip: 4 key-frame logit maps [1,C,H,W] and, per interval, stacked grids [k-1,Hg,Wg,2] x2."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    n_int = (CLIP_FRAMES - 1) // K_DELTA
+    keys = [torch.randn((1, C, H, W), device=device, generator=gen) for _ in range(n_int + 1)]
+    grids = []
+    for _ in range(n_int):
+        if mode == "linear":
+            grids.append((None, None))
+        else:
+            grids.append((make_grids(K_DELTA - 1, mode, device, gen), make_grids(K_DELTA - 1, mode, device, gen)))
+    return keys, grids
+
+
+def clip_bytes(mode):
+    n_int = (CLIP_FRAMES - 1) // K_DELTA
+    b = (n_int + 1) * S_BYTES
+    if mode == "dense":
+        b += n_int * 2 * (K_DELTA - 1) * H * W * 8
+    elif mode == "block":
+        b += n_int * 2 * (K_DELTA - 1) * (H // 16) * (W // 16) * 8
+    return b
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- device-resident arm
+def run_interval(kernels, mode, keys, grids, it, tc_prev, counts):
+    if mode == "linear":
+        labels, _ = kernels.linear_blend_argmax(keys[it], keys[it + 1], K_DELTA, tc_prev=tc_prev, counts=counts)
+    elif mode == "dense":
+        labels, _ = kernels.dense_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
+                                           counts=counts, scratch=run_interval.scratch)
+    else:
+        labels, _ = kernels.block_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
+                                           counts=counts, scratch=run_interval.scratch)
+    return labels
+
+
+run_interval.scratch = None
+
+
+def run_clip(kernels, mode, clip, counts):
+    keys, grids = clip
+    last = None
+    for it in range(len(keys) - 1):
+        labels = run_interval(kernels, mode, keys, grids, it, last, counts)
+        last = labels[K_DELTA - 1]
+    return last
+
+
+def time_resident(kernels, dist_mod, mode, clips, steps, warmup, clips_per_step, device, world, sampler=None):
+    from flood_uav_video_segmentation_b200 import launch_count
+    counts = kernels.new_counts(C, device)
+    lib = kernels.load()
+    need = max(int(lib.fuvs_dense_scratch_floats(C, H, W, K_DELTA)), int(lib.fuvs_block_scratch_floats(C, H // 16, W // 16, K_DELTA)), 1)
+    run_interval.scratch = torch.empty((need,), dtype=torch.float32, device=device)
+    ci = 0
+
+    def step():
+        nonlocal ci
+        for _ in range(clips_per_step):
+            run_clip(kernels, mode, clips[ci % len(clips)], counts)
+            ci += 1
+
+    for _ in range(warmup):
+        step()
+    counts.zero_()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx = sampler if sampler is not None else _Null()
+    with ctx:
+        e0.record()
+        for _ in range(steps):
+            step()
+        dist_mod.allreduce_counts(counts)       # the path's only collective
+        e1.record()
+        torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, launches, counts
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+# ----------------------------------------------------------------------------- end-to-end arm (host buffers)
+def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
+    """FlowBaseModel.predict_step with pinned HOST inputs: per interval H2D of both key frames and the grids on a
+    copy stream (double-buffered against compute), D2H of the uint8 label maps, counts read back at the end."""
+    from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel
+
+    class Identity(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder = torch.nn.Identity()
+            self.decoder = torch.nn.Identity()
+
+    model = FlowBaseModel(classes=C, arch="pspnet", feature_based=False, no_warp=(mode == "linear"), no_cropping=True,
+                          backbone=Identity(), output_size=(H, W), save_video=False)
+    copy_stream = torch.cuda.Stream(device)
+    n_int = (CLIP_FRAMES - 1) // K_DELTA
+    slots = []
+    for _ in range(2):
+        s = {"prev": torch.empty((1, C, H, W), device=device), "next": torch.empty((1, C, H, W), device=device),
+             "ready": torch.cuda.Event(), "free": torch.cuda.Event()}
+        if mode != "linear":
+            gshape = host_clips[0][1][0][0].shape
+            s["gl"], s["gr"] = torch.empty(gshape, device=device), torch.empty(gshape, device=device)
+        slots.append(s)
+    out_host = [torch.empty((K_DELTA, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h2d = 2 * S_BYTES + (0 if mode == "linear" else 2 * host_clips[0][1][0][0].numel() * 4)
+    d2h = K_DELTA * H * W
+    work = []   # (clip, interval)
+    ci = 0
+
+    def stage(slot, clip, it):
+        keys, grids = clip
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot["free"])
+            slot["prev"].copy_(keys[it], non_blocking=True)
+            slot["next"].copy_(keys[it + 1], non_blocking=True)
+            if mode != "linear":
+                slot["gl"].copy_(grids[it][0], non_blocking=True)
+                slot["gr"].copy_(grids[it][1], non_blocking=True)
+            slot["ready"].record(copy_stream)
+
+    def step():
+        nonlocal ci
+        items = []
+        for _ in range(clips_per_step):
+            clip = host_clips[ci % len(host_clips)]
+            ci += 1
+            items += [(clip, it) for it in range(n_int)]
+        cur = torch.cuda.current_stream(device)
+        stage(slots[0], *items[0])
+        for j, (clip, it) in enumerate(items):
+            slot = slots[j % 2]
+            if j + 1 < len(items):
+                stage(slots[(j + 1) % 2], *items[j + 1])
+            if it == 0:
+                model.last_output = None          # temporal chain resets at clip boundaries
+            cur.wait_event(slot["ready"])
+            if mode == "linear":
+                dummy = [None] * (K_DELTA - 1)
+                batch = {"frame_prev": slot["prev"], "frame_next": slot["next"], "mvs_left": dummy, "mvs_right": dummy}
+            else:
+                batch = {"frame_prev": slot["prev"], "frame_next": slot["next"],
+                         "mvs_left": _GridList(slot["gl"]), "mvs_right": _GridList(slot["gr"])}
+            labels = model.predict_step(batch, j)
+            slot["free"].record(cur)
+            out_host[j % 2].copy_(labels, non_blocking=True)          # flow/base.py:277 (already uint8)
+        return len(items)
+
+    model.on_predict_start()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        torch.distributed.barrier()
+    model.on_predict_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n_items = 0
+    for _ in range(steps):
+        n_items += step()
+    res = model.on_predict_end()              # all-reduce + D2H of the counts, fp64 formulas
+    e1.record()
+    torch.cuda.synchronize(device)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), wall_ms)    # host-side staging is part of the end-to-end cost
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    per_step_items = n_items // max(steps, 1)
+    return ms, h2d * per_step_items, d2h * per_step_items, res
+
+
+class _GridList(list):
+    """The reference's python list of k-1 grids [1,Hg,Wg,2], backed by one stacked device tensor."""
+
+    def __init__(self, stacked):
+        super().__init__(stacked[j:j + 1] for j in range(stacked.shape[0]))
+        self.stacked = stacked
+
+
+def to_host_clip(clip):
+    keys, grids = clip
+    hk = [k.cpu().pin_memory() for k in keys]
+    hg = [(None, None) if g[0] is None else (g[0].cpu().pin_memory(), g[1].cpu().pin_memory()) for g in grids]
+    return hk, hg
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_interval(mode, keys, grids, it, last):
+    """The reference call sequence on torch-CPU: FlowModel.predict -> max(1)[1] -> uint8 -> numpy temporal IoU."""
+    from oracle import flow_oracle as fo
+    from oracle import metric_oracle as mo
+    ident = torch.nn.Identity()
+    n = K_DELTA
+    if mode == "linear":
+        gl = gr = [torch.zeros(1, 1)] * (n - 1)
+    else:
+        gl = [grids[it][0][j:j + 1] for j in range(n - 1)]
+        gr = [grids[it][1][j:j + 1] for j in range(n - 1)]
+    with torch.no_grad():
+        logits = fo.predict_segmentation(ident, ident, keys[it], keys[it + 1], gl, gr, n, no_warp=(mode == "linear"))
+        labels = fo.argmax_labels(logits)
+    lab_np = labels.numpy().astype("uint8")
+    counts, new_last = mo.temporal_consistency_counts(labels.numpy(), C, 255, last)
+    return lab_np, counts, new_last
+
+
+def time_cpu(mode, host_clip, intervals, warm=1):
+    keys, grids = host_clip
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_int = len(keys) - 1
+    for w in range(warm):
+        cpu_interval(mode, keys, grids, 0, None)
+    t0 = time.perf_counter()
+    last = None
+    lab = None
+    for j in range(intervals):
+        lab, _, last = cpu_interval(mode, keys, grids, j % n_int, last if j % n_int else None)
+    dt = time.perf_counter() - t0
+    return dt, lab
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "block", "linear"])
+    ap.add_argument("--clips-per-step", type=int, default=4)
+    ap.add_argument("--distinct-clips", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-modes", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    mode = args.mode
+    workload = (f"flow-warped logit interpolation (no_warp=False), {mode} flow grids, C={C}, {H}x{W}, k={K_DELTA}, "
+                f"{CLIP_FRAMES}-frame clips" if mode != "linear" else
+                f"linear logit interpolation (no_warp=True), C={C}, {H}x{W}, k={K_DELTA}, {CLIP_FRAMES}-frame clips")
+    config = {"workload": workload, "classes": C, "height": H, "width": W, "frame_delta": K_DELTA, "mode": mode,
+              "clips_per_step": args.clips_per_step, "intervals_per_step": args.clips_per_step * 3,
+              "interpolated_frames_per_step": args.clips_per_step * 3 * (K_DELTA - 1), "parallelism": f"clip-sharded x{world}"}
+
+    if args.impl == "reference":
+        return main_reference(args, rank, world, mode, config)
+
+    from flood_uav_video_segmentation_b200 import dist as fdist
+    from flood_uav_video_segmentation_b200 import kernels
+    rank, local, world = fdist.init_from_env("nccl")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    kernels.load()
+
+    clips = [make_clip(mode, device, 1000 * rank + i) for i in range(args.distinct_clips)]
+    resident_mb = args.distinct_clips * clip_bytes(mode) / 1e6
+    config["l2_policy"] = f"inputs larger than L2: {resident_mb:.0f} MB of distinct clips cycled (L2 = 126 MB)"
+    sampler = ClockSampler(local)
+    ms, launches, counts = time_resident(kernels, fdist, mode, clips, args.steps, args.warmup, args.clips_per_step,
+                                         device, world, sampler)
+    intervals = args.steps * args.clips_per_step * 3
+    frames = intervals * (K_DELTA - 1)
+    value = frames * world / (ms / 1e3)
+    peak, peak_src = measured_peak()
+    bytes_iv = algorithmic_bytes(mode)
+    achieved = bytes_iv * intervals / (ms / 1e3) / 1e9
+    out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "impl": "ours",
+           "clocks": sampler.summary(), "gpu_launches": int(launches),
+           "output_frames_per_sec": intervals * K_DELTA * world / (ms / 1e3),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src, "kernel": f"fuvs_{mode}_interval",
+                        "algorithmic_bytes_per_launch": bytes_iv,
+                        "launch": "one interval = one C-ABI call (dense: 4 dense_step_kernel + 1 temporal_counts_kernel)",
+                        "frac_of_nominal_8000": achieved / 8000.0},
+           "miou_counts_checksum": int(counts.sum().item())}
+
+    if not args.no_modes:
+        modes = {}
+        for m in ("linear", "block", "dense"):
+            if m == mode:
+                continue
+            mclips = [make_clip(m, device, 5000 + 1000 * rank + i) for i in range(args.distinct_clips)]
+            mms, _, _ = time_resident(kernels, fdist, m, mclips, max(args.steps // 2, 10), 3, args.clips_per_step, device, world)
+            miv = max(args.steps // 2, 10) * args.clips_per_step * 3
+            mach = algorithmic_bytes(m) * miv / (mms / 1e3) / 1e9
+            modes[m] = {"value": miv * (K_DELTA - 1) * world / (mms / 1e3), "unit": "frames/s", "achieved_gbs": mach,
+                        "frac": mach / peak, "algorithmic_bytes_per_interval": algorithmic_bytes(m)}
+            del mclips
+            torch.cuda.empty_cache()
+        out["other_modes"] = modes
+
+    host_clips = None
+    if not args.no_e2e:
+        host_clips = [to_host_clip(c) for c in clips[:2]]
+        e_steps = max(min(args.steps // 10, 20), 3)
+        ems, h2d, d2h, res = time_e2e(mode, e_steps, 3, args.clips_per_step, device, world, host_clips)
+        e_frames = e_steps * args.clips_per_step * 3 * (K_DELTA - 1)
+        out["e2e"] = {"value": e_frames * world / (ems / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                      "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": ems / e_steps,
+                      "api": "FlowBaseModel.predict_step (pinned host key-frame logits + grids -> uint8 labels on host)",
+                      "temporal_miou": float(res.get("predict_miou1_epoch", float("nan")))}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        hc = host_clips[0] if host_clips else to_host_clip(clips[0])
+        n_samp = 3
+        dt, lab_cpu = time_cpu(mode, ([k.clone() for k in hc[0]], hc[1]), n_samp)
+        # same interval on the GPU for an informational label comparison (near-ties may differ: torch-CPU != torch-CUDA)
+        lab_gpu = run_interval(kernels, mode, clips[0][0], clips[0][1], (n_samp - 1) % 3, None, None)
+        mism = int((lab_gpu.cpu().numpy() != lab_cpu).sum())
+        out["cpu_baseline"] = {"value": n_samp * (K_DELTA - 1) / dt, "unit": "frames/s", "cores": torch.get_num_threads(),
+                               "kind": "port", "sample": f"{n_samp} intervals of the same {mode} workload (1 clip), "
+                               "oracle restatement of FlowModel.predict -> max(1)[1] -> numpy intersectionAndUnion on torch-CPU",
+                               "host_cpu_count": os.cpu_count(), "seconds": dt,
+                               "label_pixels_differing_from_gpu": mism, "label_pixels": int(lab_cpu.size)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main_reference(args, rank, world, mode, config):
+    """Reference arm: the reference's own CPU implementation of the path (oracle port; the Python reference cannot
+    travel to the GPU box).  One interval per step; rank 0 only."""
+    if rank != 0:
+        return
+    torch.manual_seed(0)
+    clip = make_clip(mode, torch.device("cpu"), 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(args.warmup):
+        cpu_interval(mode, clip[0], clip[1], 0, None)
+    t0 = time.perf_counter()
+    last = None
+    for s in range(args.steps):
+        _, _, last = cpu_interval(mode, clip[0], clip[1], s % 3, last if s % 3 else None)
+    dt = time.perf_counter() - t0
+    value = args.steps * (K_DELTA - 1) / dt
+    cfg = dict(config)
+    cfg["reference_step"] = "one interval (4 interpolated frames) per step on the host cores"
+    out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(args.steps, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+           "impl": "reference", "gpu_launches": 0,
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{args.steps} intervals of the {mode} workload, oracle restatement on torch-CPU"},
+           "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,7 @@ __device__ __forceinline__ int bin_of(long long v, int K, int np_bins) {
     if (v < 0 || v > K) return -1;
     return v == K ? K - 1 : static_cast<int>(v);
   }
-  if (K == 1) return (v >= -1 && v <= 1) ? 0 : -1;   // histc widens min==max to [min-1, max+1]
+  if (K == 1) return 0;   // histc(bins=1, min=0, max=0): "if min and max are both zero, the data's min and max are used" -> every value counts
   if (v < 0 || v > K - 1) return -1;                  // histc(bins=K, min=0, max=K-1) ignores outliers
   return static_cast<int>(v);
 }

@@ -43,11 +43,12 @@ def intersection_and_union_torch(output, target, K, ignore_index=255):
 def _histc_ints(v, K):
     """torch.histc(bins=K, min=0, max=K-1) on integer data: ATen SummaryOps.cu getBin():
     bin = (v - min) * bins / (max - min) in integer arithmetic, bin == bins folded into the last bin, values
-    outside [min, max] ignored; min == max is widened to [min-1, max+1]."""
+    outside [min, max] ignored.  K == 1 gives min == max == 0, which torch.histc documents as "use the data's
+    min and max": every element lands in the single bin (confirmed against torch-CUDA on the B200)."""
     v = np.asarray(v).astype(np.int64).reshape(-1)
+    if K == 1:
+        return np.array([v.size], dtype=np.int64)
     lo, hi = 0, K - 1
-    if lo == hi:
-        lo, hi = lo - 1, hi + 1
     keep = (v >= lo) & (v <= hi)
     b = (v[keep] - lo) * K // (hi - lo)
     b[b == K] = K - 1

@@ -1,0 +1,256 @@
+"""Parity of every C-ABI entry point against the oracle (oracle/flow_oracle.py, oracle/metric_oracle.py) on the
+same seeded inputs.  Bit-exact for label maps, counts and (against torch-CUDA on the same device) logits; the
+torch-CPU oracle is matched within 1e-5 relative for warp modes (torch's CPU and CUDA grid_sample differ)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flood_uav_video_segmentation_b200 import kernels
+from flood_uav_video_segmentation_b200.synthetic import clip_keyframes, flow_grids, gt_labels, keyframe_logits
+from oracle import flow_oracle as fo
+from oracle import metric_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+ident = torch.nn.Identity()
+
+
+def bits_equal(a, b):
+    return a.shape == b.shape and bool((a.contiguous().view(torch.int32) == b.contiguous().view(torch.int32)).all())
+
+
+def oracle_interval(o, o_next, gl, gr, n, no_warp, device):
+    """Reference call sequence on `device` with identity encoder/decoder: logits [n,C,h,w], labels int64."""
+    o, o_next = o.to(device), o_next.to(device)
+    gl = [g.to(device) for g in gl]
+    gr = [g.to(device) for g in gr]
+    logits = fo.predict_segmentation(ident, ident, o, o_next, gl, gr, n, no_warp=no_warp)
+    return logits, fo.argmax_labels(logits)
+
+
+def oracle_temporal(labels_i64, K, last=None):
+    lab = labels_i64.cpu().numpy()
+    (i, u, t), new_last = mo.temporal_consistency_counts(lab, K, 255, last)
+    return np.stack([i, u, t]), new_last
+
+
+SHAPES = [(5, 433, 433), (2, 433, 433), (5, 64, 96), (5, 37, 53), (3, 270, 480), (7, 48, 64), (12, 40, 40)]
+
+
+@pytest.mark.parametrize("C,H,W", SHAPES)
+@pytest.mark.parametrize("n", [2, 5])
+def test_linear_interval(cuda, C, H, W, n):
+    o, o_next = keyframe_logits(C, H, W, 0, 0)[None], keyframe_logits(C, H, W, 0, 1)[None]
+    dummy = [torch.zeros(1, 1)] * (n - 1)
+    ref_logits, ref_labels = oracle_interval(o, o_next, dummy, dummy, n, True, cuda)
+    cpu_logits, cpu_labels = oracle_interval(o, o_next, dummy, dummy, n, True, "cpu")
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), n, want_labels=True, want_logits=True,
+                                                 tc_prev=tc_prev.to(cuda), counts=counts)
+    assert bits_equal(logits, ref_logits), "logits differ from torch-CUDA oracle"
+    assert bits_equal(logits.cpu(), cpu_logits), "linear mode must also be bit-equal to torch-CPU"
+    assert torch.equal(labels.long(), ref_labels)
+    assert torch.equal(labels.cpu().long(), cpu_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    # labels only / counts without tc_prev
+    counts2 = kernels.new_counts(C, cuda)
+    labels2, none = kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), n, counts=counts2)
+    assert none is None and torch.equal(labels2, labels)
+    ref_counts2, _ = oracle_temporal(ref_labels, C, None)
+    assert np.array_equal(counts2.cpu().numpy(), ref_counts2)
+
+
+@pytest.mark.parametrize("C,H,W", [(5, 433, 433), (2, 270, 480), (5, 64, 96), (5, 37, 53), (6, 48, 64)])
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6])
+def test_dense_interval(cuda, C, H, W, n):
+    o, o_next = keyframe_logits(C, H, W, 1, 0)[None], keyframe_logits(C, H, W, 1, 1)[None]
+    gl = flow_grids(H, W, n, "dense", clip=1, side=0)
+    gr = flow_grids(H, W, n, "dense", clip=1, side=1)
+    ref_logits, ref_labels = oracle_interval(o, o_next, gl, gr, n, False, cuda)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.dense_interval(o.to(cuda), o_next.to(cuda), [g.to(cuda) for g in gl],
+                                            [g.to(cuda) for g in gr], n, want_labels=True, want_logits=True,
+                                            counts=counts)
+    bad = int((logits.view(torch.int32) != ref_logits.view(torch.int32)).sum())
+    assert bad == 0, f"{bad} logits differ from torch-CUDA oracle"
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, None)
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    cpu_logits, _ = oracle_interval(o, o_next, gl, gr, n, False, "cpu")
+    torch.testing.assert_close(logits.cpu(), cpu_logits, rtol=1e-4, atol=1e-4)   # torch-CPU vs torch-CUDA kernels differ
+
+
+@pytest.mark.parametrize("C,H,W", [(5, 433, 433), (2, 272, 480), (5, 64, 96), (5, 37, 53), (6, 48, 64)])
+@pytest.mark.parametrize("n", [2, 5, 7])
+def test_block_interval(cuda, C, H, W, n):
+    o, o_next = keyframe_logits(C, H, W, 2, 0)[None], keyframe_logits(C, H, W, 2, 1)[None]
+    gl = flow_grids(H, W, n, "block", clip=2, side=0)
+    gr = flow_grids(H, W, n, "block", clip=2, side=1)
+    ref_logits, ref_labels = oracle_interval(o, o_next, gl, gr, n, False, cuda)
+    counts = kernels.new_counts(C, cuda)
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(6), dtype=torch.uint8)
+    labels, logits = kernels.block_interval(o.to(cuda), o_next.to(cuda), [g.to(cuda) for g in gl],
+                                            [g.to(cuda) for g in gr], n, want_labels=True, want_logits=True,
+                                            tc_prev=tc_prev.to(cuda), counts=counts)
+    bad = int((logits.view(torch.int32) != ref_logits.view(torch.int32)).sum())
+    assert bad == 0, f"{bad} logits differ from torch-CUDA oracle"
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    cpu_logits, _ = oracle_interval(o, o_next, gl, gr, n, False, "cpu")
+    torch.testing.assert_close(logits.cpu(), cpu_logits, rtol=1e-4, atol=1e-4)   # torch-CPU vs torch-CUDA kernels differ
+
+
+def test_full_size_1080p_all_modes(cuda):
+    """BASELINE.json configs at full size, one interval each, against the oracle on torch-CUDA."""
+    C, H, W, n = 5, 1080, 1920, 5
+    ks = clip_keyframes(C, H, W, n, frames=6, clip=3)
+    o, o_next = ks[0].to(cuda), ks[1].to(cuda)
+    for mode in ("linear", "block", "dense"):
+        if mode == "linear":
+            gl = gr = [torch.zeros(1, 1)] * (n - 1)
+            labels, _ = kernels.linear_blend_argmax(o, o_next, n)
+        else:
+            gl = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=3, side=0)]
+            gr = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=3, side=1)]
+            fn = kernels.block_interval if mode == "block" else kernels.dense_interval
+            labels, _ = fn(o, o_next, gl, gr, n)
+        ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o, o_next, gl, gr, n, no_warp=(mode == "linear")))
+        diff = int((labels.long() != ref).sum())
+        assert diff == 0, f"{mode}: {diff} label pixels differ at 1080p"
+        del ref
+        torch.cuda.empty_cache()
+
+
+def test_argmax_ties_and_nan(cuda):
+    C, H, W = 5, 8, 16
+    x = torch.zeros(1, C, H, W)
+    x[0, :, 0, 0] = torch.tensor([1.0, 3.0, 3.0, 2.0, 3.0])           # tie -> lowest index
+    x[0, :, 0, 1] = torch.tensor([1.0, float("nan"), 5.0, float("nan"), 0.0])  # NaN beats numbers, first NaN
+    x[0, :, 0, 2] = torch.tensor([-0.0, 0.0, -0.0, 0.0, -0.0])          # -0 == +0 -> index 0
+    x[0, :, 0, 3] = torch.tensor([float("-inf")] * 5)
+    x[0, :, 0, 4] = torch.tensor([0.0, float("inf"), float("inf"), 1.0, 2.0])
+    x[0, :, 1:, :] = torch.randn(C, H - 1, W, generator=torch.Generator().manual_seed(3)).round()  # many ties
+    xc = x.to(cuda)
+    ref = xc.max(1)[1]
+    assert torch.equal(kernels.argmax(xc).long(), ref)
+    assert torch.equal(kernels.argmax(xc, dtype=torch.int64), ref)
+    labels, _ = kernels.linear_blend_argmax(xc, xc, 3)
+    ref3 = fo.argmax_labels(fo.predict_segmentation(ident, ident, xc, xc, [torch.zeros(1, 1)] * 2, [torch.zeros(1, 1)] * 2, 3, True))
+    assert torch.equal(labels.long(), ref3)
+
+
+@pytest.mark.parametrize("shape", [((5, 67, 120), (1072, 1920)), ((3, 55, 55), (433, 433)), ((2, 9, 7), (10, 8)),
+                                   ((4, 33, 33), (33, 33)), ((2, 1, 1), (5, 7)), ((2, 6, 6), (1, 1))])
+def test_upsample(cuda, shape):
+    (C, Hin, Win), (Ho, Wo) = shape
+    x = torch.randn(2, C, Hin, Win, generator=torch.Generator().manual_seed(9)).to(cuda)
+    ref = F.interpolate(x, size=(Ho, Wo), mode="bilinear", align_corners=True)
+    assert bits_equal(kernels.upsample_bilinear_ac(x, (Ho, Wo)), ref)
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_warp_step(cuda, align):
+    C, H, W = 6, 135, 240
+    x = torch.randn(1, C, H, W, generator=torch.Generator().manual_seed(11)).to(cuda)
+    g = flow_grids(1072, 1920, 2, "block", clip=4, jitter=0.1)[0].to(cuda)
+    ref = F.grid_sample(x, g, mode="bilinear", padding_mode="border", align_corners=align)
+    out, _ = kernels.warp_step(x[0], g, align_corners=align)
+    assert bits_equal(out, ref[0])
+    # two-sided launch, many channels (feature-map shape class)
+    xf = torch.randn(2, 300, 34, 60, generator=torch.Generator().manual_seed(12)).to(cuda)
+    g2 = flow_grids(272, 480, 3, "block", clip=5, jitter=0.2)
+    a, b = kernels.warp_step(xf[0], g2[0].to(cuda), xf[1], g2[1].to(cuda), align_corners=align)
+    assert bits_equal(a, F.grid_sample(xf[0:1], g2[0].to(cuda), mode="bilinear", padding_mode="border", align_corners=align)[0])
+    assert bits_equal(b, F.grid_sample(xf[1:2], g2[1].to(cuda), mode="bilinear", padding_mode="border", align_corners=align)[0])
+
+
+def test_warp_step_special_coordinates(cuda):
+    """NaN / Inf / far out-of-range grid values and Inf source pixels at the border (skipped taps)."""
+    C, H, W = 2, 5, 6
+    x = torch.arange(C * H * W, dtype=torch.float32).reshape(1, C, H, W)
+    x[0, 0, 0, W - 1] = float("inf")
+    x[0, 1, H - 1, 0] = float("nan")
+    g = torch.tensor([[-1.0, -1.0], [1.0, 1.0], [float("nan"), 0.0], [float("inf"), float("-inf")], [5.0, -7.0],
+                      [1.0, -1.0], [-1.0, 1.0], [0.999, 0.3], [0.0, 0.0]]).reshape(1, 3, 3, 2)
+    ref = F.grid_sample(x.to(cuda), g.to(cuda), mode="bilinear", padding_mode="border", align_corners=False)
+    out, _ = kernels.warp_step(x[0].to(cuda), g.to(cuda))
+    assert torch.equal(torch.isnan(out), torch.isnan(ref[0]))
+    assert bits_equal(torch.nan_to_num(out, nan=7.0), torch.nan_to_num(ref[0], nan=7.0))
+
+
+def test_blend_argmax(cuda):
+    a = torch.randn(3, 5, 37, 53, generator=torch.Generator().manual_seed(1)).to(cuda)
+    b = torch.randn(3, 5, 37, 53, generator=torch.Generator().manual_seed(2)).to(cuda)
+    wa, wb = 3 / 7, 4 / 7
+    ref = wa * a + wb * b
+    out, labels = kernels.blend_argmax(a, b, wa, wb, want_labels=True)
+    assert bits_equal(out, ref) and torch.equal(labels.long(), ref.max(1)[1])
+    out1, _ = kernels.blend_argmax(a, None, wa, 0.0)
+    assert bits_equal(out1, a * wa)
+
+
+@pytest.mark.parametrize("K", [5, 2, 1, 19])
+@pytest.mark.parametrize("pdt,tdt", [(torch.int64, torch.int64), (torch.uint8, torch.int64), (torch.uint8, torch.uint8)])
+def test_confusion_vs_oracle(cuda, K, pdt, tdt):
+    H, W = 211, 307
+    g = torch.Generator().manual_seed(K)
+    pred = torch.randint(0, K, (2, H, W), generator=g).to(pdt)
+    target = torch.randint(0, K + 3, (2, H, W), generator=g)     # includes out-of-range classes K..K+2
+    target[torch.rand(2, H, W, generator=g) < 0.05] = 255
+    target = target.to(tdt)
+    # numpy convention (util/util.py:36-47)
+    i, u, t = mo.intersection_and_union_np(pred.numpy(), target.numpy(), K, 255)
+    got = kernels.confusion(pred.to(cuda), target.to(cuda), K, 255, numpy_bins=True).cpu().numpy()
+    assert np.array_equal(got, np.stack([i, u, t]))
+    # torch.histc convention (util/util.py:52-63), restated integer binning
+    i, u, t = mo.intersection_and_union_histc_ints(pred.numpy(), target.numpy(), K, 255)
+    pc = pred.to(cuda)
+    got = kernels.confusion(pc, target.to(cuda), K, 255, mutate_pred=True).cpu().numpy()
+    assert np.array_equal(got, np.stack([i, u, t]))
+    # in-place ignore substitution on the caller's tensor (util/util.py:57)
+    exp = pred.clone()
+    exp[target == 255] = 255
+    assert torch.equal(pc.cpu(), exp)
+    if pdt == torch.int64 and tdt == torch.int64:
+        # the real thing: torch.histc on int64 exists only on CUDA
+        o2 = pred.to(cuda).clone()
+        ri, ru, rt = mo.intersection_and_union_torch(o2, target.to(cuda), K, 255)
+        assert np.array_equal(got, torch.stack([ri, ru, rt]).cpu().numpy().astype(np.int64))
+
+
+def test_confusion_accumulates_and_ragged(cuda):
+    K = 5
+    counts = kernels.new_counts(K, cuda)
+    tot = np.zeros((3, K), np.int64)
+    for N in (0, 1, 31, 33, 1000, 4097):
+        g = torch.Generator().manual_seed(N)
+        pred = torch.randint(0, K, (N,), generator=g)
+        target = torch.randint(0, K, (N,), generator=g)
+        if N:
+            kernels.confusion(pred.to(cuda), target.to(cuda), K, 255, counts=counts)
+            tot += np.stack(mo.intersection_and_union_histc_ints(pred.numpy(), target.numpy(), K, 255))
+    assert np.array_equal(counts.cpu().numpy(), tot)
+
+
+@pytest.mark.parametrize("K,H,W", [(5, 433, 433), (5, 64, 96), (12, 37, 53)])
+def test_temporal_counts(cuda, K, H, W):
+    g = torch.Generator().manual_seed(K + H)
+    labels = torch.randint(0, K, (6, H, W), generator=g, dtype=torch.uint8)
+    last = torch.randint(0, K, (H, W), generator=g, dtype=torch.uint8)
+    for prev in (None, last):
+        ref, _ = oracle_temporal(labels.long(), K, None if prev is None else prev.numpy().astype(np.int64))
+        got = kernels.temporal_counts(labels.to(cuda), K, 255, tc_prev=None if prev is None else prev.to(cuda))
+        assert np.array_equal(got.cpu().numpy(), ref)
+
+
+def test_errors_are_loud(cuda):
+    with pytest.raises(kernels.FuvsError):
+        kernels.linear_blend_argmax(torch.zeros(5, 8, 8), torch.zeros(5, 8, 8), 5)          # CPU tensors
+    with pytest.raises(kernels.FuvsError):
+        kernels.linear_blend_argmax(torch.zeros(5, 8, 8, device=cuda), torch.zeros(5, 8, 8, device=cuda), 500)
+    with pytest.raises(kernels.FuvsError):
+        kernels.confusion(torch.zeros(4, device=cuda), torch.zeros(4, dtype=torch.int64, device=cuda), 5)
