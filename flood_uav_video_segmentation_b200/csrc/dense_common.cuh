@@ -1,0 +1,28 @@
+// dense_common.cuh — launch description shared by the two dense-step kernels
+// (warp.cu: direct L1 gather; dense_tma.cu: TMA-staged shared-memory gather).
+#pragma once
+#include "fuvs_common.cuh"
+
+namespace fuvs {
+
+// One lock-step warp step j of a dense interval (see warp.cu header comment).
+struct DenseStep {
+  const float* srcL; const float* srcR;      // states j-1, [C,H,W]
+  const float* gridL; const float* gridR;    // [H,W,2]
+  float* dstL; float* dstR;                  // states j or NULL (last step)
+  // frame A = frame j   : wA0 * L_j(reg)      + wA1 * R_{n-j} (pointR, or this step's R if NULL)
+  // frame B = frame n-j : wB0 * L_{n-j}(pointL) + wB1 * R_j(reg)
+  int emitA, emitB;
+  const float* pointR; const float* pointL;
+  float wA0, wA1, wB0, wB1;
+  uint8_t* labelA; uint8_t* labelB;
+  float* logitA; float* logitB;
+  // frame 0 on step 1
+  const float* key0; uint8_t* label0; float* logit0;
+};
+
+// dense_tma.cu: returns FUVS_OK if it ran the step, 1 if the shape is not eligible (caller uses the direct kernel),
+// negative on error.
+int launch_dense_step_tma(const DenseStep& a, int C, int H, int W, cudaStream_t st);
+
+}  // namespace fuvs

@@ -141,6 +141,39 @@ __device__ __forceinline__ float blend2(float wa, float a, float wb, float b) {
 }
 
 // ---------------------------------------------------------------------------
+// packed FP32x2 arithmetic (Blackwell FMUL2 / FFMA2): two IEEE-rn fp32 results
+// per instruction, which halves the issue slots of the blend.
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though the
+// .rn forms must not fuse (checked in SASS), which would break bit-exactness.
+// The add is therefore written as fma(p, one, q) with `one` a RUN-TIME 1.0f
+// (a kernel argument): p*1 is exact, so the result is rn(p+q), and ptxas
+// cannot fold a multiplier it does not know.
+// ---------------------------------------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 mul2_rn(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2_rn(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// {fl(fl(a.lo*wa)+fl(b.lo*wb)), fl(fl(a.hi*wa)+fl(b.hi*wb))}; wa2/wb2/one2 hold the scalar in both halves
+__device__ __forceinline__ u64 blend2x2(u64 wa2, u64 a, u64 wb2, u64 b, u64 one2) {
+  return fma2_rn(mul2_rn(a, wa2), one2, mul2_rn(b, wb2));
+}
+
+// ---------------------------------------------------------------------------
 // arg-max over classes with torch.max(dim) semantics (flow/base.py:147,167,276):
 // lowest index wins ties, a NaN beats every number, the first NaN stays.
 // ---------------------------------------------------------------------------
@@ -159,6 +192,7 @@ struct ArgMax {
 // ---------------------------------------------------------------------------
 struct GsTap {
   int off00;        // iy_nw * Win + ix_nw (always in bounds in border mode)
+  int ix, iy;       // the north-west corner itself
   int dx, dy;       // 1 if the east / south neighbour is in bounds, else 0
   float nw, ne, sw, se;
 };
@@ -195,6 +229,8 @@ __device__ __forceinline__ GsTap gs_setup(float gx, float gy, int Hin, int Win, 
   t.dx = (ix_nw + 1 < Win) ? 1 : 0;
   t.dy = (iy_nw + 1 < Hin) ? 1 : 0;
   t.off00 = iy_nw * Win + ix_nw;
+  t.ix = ix_nw;
+  t.iy = iy_nw;
   return t;
 }
 

@@ -100,6 +100,210 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
   if (COUNTS) block_flush_counts<CT>(tot, sh, counts, CT);
 }
 
+// ---------------------------------------------------------------------------
+// Fast path: 4 pixels per thread (HW % 4 == 0), C in {2,3,4,5,8}, ignore_index
+// outside [0,C).  Instruction diet (the first version was issue-bound at 1491
+// instructions per thread, profiles/r01_ncu_linear_v1.txt):
+//   * blends on packed FP32x2 (3 FMUL2/FFMA2 per pixel pair and class);
+//   * arg-max without NaN handling when all 2*C*4 inputs are finite (then no
+//     blend can be NaN); a thread that sees Inf/NaN takes the exact slow path;
+//   * counts in three 32-bit registers with FW-bit fields (one shift + three
+//     adds per label), spilled to per-thread 32-bit totals before a field can
+//     overflow and REDUX-reduced once at the end of the kernel.
+// ---------------------------------------------------------------------------
+template <int K> struct FieldCfg {
+  static constexpr int FW = (K <= 4) ? 8 : (K <= 5 ? 6 : 4);
+  static constexpr unsigned MASK = (1u << FW) - 1u;
+  static constexpr int FLUSH_FRAMES = static_cast<int>(MASK) / 4;   // 4 labels per frame and thread
+};
+
+// arg-max of 4 pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
+template <int CT, bool NANSAFE>
+__device__ __forceinline__ void argmax4(const float (&x)[CT][4], int (&lab)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float best = x[0][i];
+    int idx = 0;
+#pragma unroll
+    for (int c = 1; c < CT; ++c) {
+      const float v = x[c][i];
+      bool take = v > best;
+      if (NANSAFE) take = take || ((v != v) && (best == best));
+      best = take ? v : best;
+      idx = take ? c : idx;
+    }
+    lab[i] = idx;
+  }
+}
+
+template <int CT>
+struct LinCounts {
+  using FC = FieldCfg<CT>;
+  unsigned accI, accO, accT;
+  unsigned totI[CT], totO[CT], totT[CT];
+  __device__ __forceinline__ void init() {
+    accI = accO = accT = 0u;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { totI[c] = 0u; totO[c] = 0u; totT[c] = 0u; }
+  }
+  __device__ __forceinline__ void spill() {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      totI[c] += (accI >> (FC::FW * c)) & FC::MASK;
+      totO[c] += (accO >> (FC::FW * c)) & FC::MASK;
+      totT[c] += (accT >> (FC::FW * c)) & FC::MASK;
+    }
+    accI = accO = accT = 0u;
+  }
+  // label `lab` of the current frame against `last` (field value flast) of the previous one
+  __device__ __forceinline__ void add(int lab, unsigned fo, int last, unsigned flast) {
+    accO += fo;
+    accT += flast;
+    accI += (lab == last) ? fo : 0u;
+  }
+};
+
+template <int CT, bool COUNTS, bool NANSAFE>
+__device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&a23)[CT], const u64 (&b01)[CT],
+                                              const u64 (&b23)[CT], long long HW, long long pix, int n,
+                                              uint8_t* __restrict__ labels, float* __restrict__ logits,
+                                              const uint8_t* __restrict__ tc_prev, int ignore_index,
+                                              const BlendWeights& wts, u64 one2, LinCounts<CT>& cnt) {
+  using FC = FieldCfg<CT>;
+  int last[4];
+  unsigned flast[4];
+  // ---- frame 0: the unblended key frame (flow/model.py:195-197)
+  {
+    float x[CT][4];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      unpack2(a01[c], x[c][0], x[c][1]);
+      unpack2(a23[c], x[c][2], x[c][3]);
+      if (logits) __stcs(reinterpret_cast<float4*>(logits + c * HW + pix), make_float4(x[c][0], x[c][1], x[c][2], x[c][3]));
+    }
+    int lab[4];
+    argmax4<CT, NANSAFE>(x, lab);
+    if (labels)
+      *reinterpret_cast<unsigned*>(labels + pix) =
+          (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+    if (COUNTS) {
+      if (tc_prev != nullptr) {
+        const unsigned t = __ldg(reinterpret_cast<const unsigned*>(tc_prev + pix));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tl = (t >> (8 * i)) & 255u;
+          const unsigned ft = (tl < CT) ? (1u << (FC::FW * tl)) : 0u;
+          // output[target == ignore] = ignore, and ignore is outside [0,CT) on this path: nothing of this pixel counts
+          const unsigned fo = (tl == ignore_index) ? 0u : (1u << (FC::FW * lab[i]));
+          cnt.add(lab[i], fo, tl, ft);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        last[i] = lab[i];
+        flast[i] = 1u << (FC::FW * lab[i]);
+      }
+    }
+  }
+  // ---- frames 1..n-1: fl(fl(w0*a) + fl(w1*b))  (flow/model.py:233-237)
+  int since_spill = 1;
+  for (int p = 1; p < n; ++p) {
+    const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
+    float* lg = logits ? logits + (static_cast<long long>(p) * CT) * HW + pix : nullptr;
+    float x[CT][4];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      unpack2(blend2x2(w0, a01[c], w1, b01[c], one2), x[c][0], x[c][1]);
+      unpack2(blend2x2(w0, a23[c], w1, b23[c], one2), x[c][2], x[c][3]);
+      if (lg) __stcs(reinterpret_cast<float4*>(lg + c * HW), make_float4(x[c][0], x[c][1], x[c][2], x[c][3]));
+    }
+    int lab[4];
+    argmax4<CT, NANSAFE>(x, lab);
+    if (labels)
+      *reinterpret_cast<unsigned*>(labels + static_cast<long long>(p) * HW + pix) =
+          (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+    if (COUNTS) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned fo = 1u << (FC::FW * lab[i]);
+        cnt.add(lab[i], fo, last[i], flast[i]);
+        last[i] = lab[i];
+        flast[i] = fo;
+      }
+      if (++since_spill >= FC::FLUSH_FRAMES) {
+        cnt.spill();
+        since_spill = 0;
+      }
+    }
+  }
+  if (COUNTS) cnt.spill();
+}
+
+template <int CT, bool COUNTS>
+__global__ void __launch_bounds__(256, 2)
+linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __restrict__ next,
+                              long long HW, int n,
+                              uint8_t* __restrict__ labels, float* __restrict__ logits,
+                              const uint8_t* __restrict__ tc_prev,
+                              unsigned long long* __restrict__ counts, int ignore_index,
+                              const BlendWeights wts, float one) {
+  __shared__ unsigned sh[24];
+  const long long nvec = HW >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const u64 one2 = pack2(one, one);
+  const float zero = __fsub_rn(one, one);          // run-time 0 (see the note on ptxas in fuvs_common.cuh)
+  const u64 zero2 = pack2(zero, zero);
+  LinCounts<CT> cnt;
+  cnt.init();
+
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const long long pix = v << 2;
+    u64 a01[CT], a23[CT], b01[CT], b23[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(prev + c * HW + pix));
+      a01[c] = pack2(t.x, t.y);
+      a23[c] = pack2(t.z, t.w);
+    }
+    if (n > 1) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(next + c * HW + pix));
+        b01[c] = pack2(t.x, t.y);
+        b23[c] = pack2(t.z, t.w);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) { b01[c] = zero2; b23[c] = zero2; }
+    }
+    // x*0 is 0 for finite x and NaN for Inf/NaN: one FFMA2 per pixel pair detects non-finite inputs
+    u64 probe = zero2;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      probe = fma2_rn(a01[c], zero2, probe);
+      probe = fma2_rn(a23[c], zero2, probe);
+      probe = fma2_rn(b01[c], zero2, probe);
+      probe = fma2_rn(b23[c], zero2, probe);
+    }
+    float pr0, pr1;
+    unpack2(probe, pr0, pr1);
+    if ((pr0 == pr0) && (pr1 == pr1))
+      linear_frames<CT, COUNTS, false>(a01, a23, b01, b23, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+    else
+      linear_frames<CT, COUNTS, true>(a01, a23, b01, b23, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+  }
+  if (COUNTS) {
+    WarpTotals<CT> wt;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      wt.I[c] = __reduce_add_sync(0xffffffffu, cnt.totI[c]);
+      wt.O[c] = __reduce_add_sync(0xffffffffu, cnt.totO[c]);
+      wt.T[c] = __reduce_add_sync(0xffffffffu, cnt.totT[c]);
+    }
+    block_flush_counts<CT>(wt, sh, counts, CT);
+  }
+}
+
 // Generic class count (C <= 256 when labels/counts are requested): class loop
 // inside the frame loop, key-frame values re-read through L1.
 template <int VEC>
@@ -160,10 +364,28 @@ linear_blend_argmax_generic_kernel(const float* __restrict__ prev, const float* 
   if (do_counts) smem_hist_flush(sh, counts, C);
 }
 
+template <int CT, bool COUNTS>
+static int launch_v4(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
+                     const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
+                     cudaStream_t st) {
+  const int threads = 256;
+  const long long need = ((HW >> 2) + threads - 1) / threads;
+  static int bps = blocks_per_sm(linear_blend_argmax_v4_kernel<CT, COUNTS>, threads);
+  const long long cap = static_cast<long long>(sm_count()) * bps;
+  const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
+  linear_blend_argmax_v4_kernel<CT, COUNTS><<<grid, threads, 0, st>>>(
+      prev, next, HW, n, labels, logits, tc_prev, reinterpret_cast<unsigned long long*>(counts), ignore_index, w, 1.0f);
+  return check_launch("fuvs_linear_blend_argmax");
+}
+
 template <int CT, int VEC>
 static int launch_fixed(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                         cudaStream_t st) {
+  if (VEC == 4 && (ignore_index < 0 || ignore_index >= CT)) {
+    if (counts) return launch_v4<CT, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    return launch_v4<CT, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+  }
   const long long nvec = HW / VEC;
   const int threads = 256;
   long long need = (nvec + threads - 1) / threads;

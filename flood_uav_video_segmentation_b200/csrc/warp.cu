@@ -13,7 +13,9 @@
 // max(p, n-p): the state produced in that step is still in registers, the
 // other one is re-read pointwise.  States n-1 are never written; frame 0
 // (arg-max of the key frame) rides on step 1.
-#include "fuvs_common.cuh"
+#include <cstdlib>
+
+#include "dense_common.cuh"
 
 namespace fuvs {
 
@@ -78,21 +80,6 @@ static int launch_warp_step(const float* src0, const float* grid0, float* dst0, 
 // ---------------------------------------------------------------------------
 // dense lock-step kernel
 // ---------------------------------------------------------------------------
-struct DenseStep {
-  const float* srcL; const float* srcR;      // states j-1, [C,H,W]
-  const float* gridL; const float* gridR;    // [H,W,2]
-  float* dstL; float* dstR;                  // states j or NULL (last step)
-  // frame A = frame j      : wA0 * L_j(reg)   + wA1 * R_{n-j} (pointR, or this step's R if NULL)
-  // frame B = frame n-j    : wB0 * L_{n-j}(pointL) + wB1 * R_j(reg)
-  int emitA, emitB;
-  const float* pointR; const float* pointL;
-  float wA0, wA1, wB0, wB1;
-  uint8_t* labelA; uint8_t* labelB;
-  float* logitA; float* logitB;
-  // frame 0 on step 1
-  const float* key0; uint8_t* label0; float* logit0;
-};
-
 template <class NM, int CT>
 __global__ void __launch_bounds__(256)
 dense_step_kernel(const DenseStep A, int Crt, int H, int W) {
@@ -203,6 +190,8 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
   } else {
     BlendWeights w;
     make_blend_weights(n, &w);
+    // FUVS_DENSE_KERNEL=direct forces the L1-gather kernel (A/B measurements); default is the TMA-staged one
+    static const bool use_tma = []() { const char* e = getenv("FUVS_DENSE_KERNEL"); return !(e && e[0] == 'd'); }();
     float* Lst = scratch;                       // states 1..n-2
     float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
     for (int j = 1; j <= n - 1; ++j) {
@@ -234,7 +223,11 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
         a.label0 = labels;
         a.logit0 = logits;
       }
-      if (int e = launch_dense_step<Nm>(a, C, H, W, st)) return e;
+      const int r = use_tma ? launch_dense_step_tma(a, C, H, W, st) : 1;
+      if (r < 0) return r;
+      if (r > 0) {   // not eligible for the TMA-staged kernel: direct-gather kernel
+        if (int e = launch_dense_step<Nm>(a, C, H, W, st)) return e;
+      }
     }
   }
   if (counts) return launch_temporal_counts(labels, n, HW, tc_prev, C, ignore_index, counts, st);

@@ -104,6 +104,30 @@ def test_block_interval(cuda, C, H, W, n):
     torch.testing.assert_close(logits.cpu(), cpu_logits, rtol=1e-4, atol=1e-4)   # torch-CPU vs torch-CUDA kernels differ
 
 
+@pytest.mark.parametrize("jitter", [0.05, 0.3, 1.5])
+@pytest.mark.parametrize("C,H,W,n", [(5, 272, 480, 5), (2, 96, 256, 4), (7, 64, 132, 3)])
+def test_dense_interval_tma_path_and_large_motion(cuda, jitter, C, H, W, n):
+    """W % 4 == 0 shapes take the TMA-staged kernel; large jitter pushes taps outside the staged box (global-gather
+    branch of the same kernel) and far outside the image (border clip)."""
+    o, o_next = keyframe_logits(C, H, W, 4, 0)[None], keyframe_logits(C, H, W, 4, 1)[None]
+    gl = flow_grids(H, W, n, "dense", clip=4, side=0, jitter=jitter)
+    gr = flow_grids(H, W, n, "dense", clip=4, side=1, jitter=jitter)
+    ref_logits, ref_labels = oracle_interval(o, o_next, gl, gr, n, False, cuda)
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(2), dtype=torch.uint8)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.dense_interval(o.to(cuda), o_next.to(cuda), [g.to(cuda) for g in gl],
+                                            [g.to(cuda) for g in gr], n, want_labels=True, want_logits=True,
+                                            tc_prev=tc_prev.to(cuda), counts=counts)
+    bad = int((logits.view(torch.int32) != ref_logits.view(torch.int32)).sum())
+    assert bad == 0, f"{bad} logits differ from torch-CUDA oracle"
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    # labels-only call (no logits materialised) gives the same maps
+    labels2, _ = kernels.dense_interval(o.to(cuda), o_next.to(cuda), [g.to(cuda) for g in gl], [g.to(cuda) for g in gr], n)
+    assert torch.equal(labels2, labels)
+
+
 def test_full_size_1080p_all_modes(cuda):
     """BASELINE.json configs at full size, one interval each, against the oracle on torch-CUDA."""
     C, H, W, n = 5, 1080, 1920, 5
