@@ -11,6 +11,10 @@
 // the previous low-resolution state (flow/model.py:214-215).  All 2(n-1) states
 // stay L2-resident; one streaming kernel then up-samples the two states each
 // frame needs (align_corners=True), blends, arg-maxes and writes the labels.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "fuvs_common.cuh"
 
 namespace fuvs {
@@ -140,6 +144,232 @@ block_stream_kernel(const float* __restrict__ key0, const float* __restrict__ Ls
   }
 }
 
+// ---------------------------------------------------------------------------
+// Whole low-resolution chain in ONE launch: a thread-block cluster per side (8 CTAs x 1024 threads cover the 8 040
+// grid points of a 67x120 grid with one point per thread), cluster.sync() between the n-1 dependent steps instead
+// of n-1 kernel launches.  cluster.sync() is a release/acquire barrier at cluster scope (and invalidates L1), so the
+// states written in step j are visible to every CTA of the cluster in step j+1; they are read with ld.global.cg.
+// ---------------------------------------------------------------------------
+constexpr int CHAIN_CLUSTER = 8;
+constexpr int CHAIN_THREADS = 1024;
+
+template <class NM>
+__device__ __forceinline__ float gs_fetch_cg(const float* plane, const GsTap& t, int Win) {
+  const float* p = plane + t.off00;
+  const float v00 = __ldcg(p), v01 = __ldcg(p + t.dx), v10 = __ldcg(p + t.dy * Win), v11 = __ldcg(p + t.dy * Win + t.dx);
+  float acc = 0.f;
+  acc = tap_acc<NM>(acc, v00, t.nw);
+  if (t.dx) acc = tap_acc<NM>(acc, v01, t.ne);
+  if (t.dy) acc = tap_acc<NM>(acc, v10, t.sw);
+  if (t.dx & t.dy) acc = tap_acc<NM>(acc, v11, t.se);
+  return acc;
+}
+
+template <class NM>
+__global__ void __cluster_dims__(CHAIN_CLUSTER, 1, 1) __launch_bounds__(CHAIN_THREADS)
+block_chain_cluster_kernel(const float* __restrict__ prev, const float* __restrict__ next,
+                           const float* __restrict__ grids_left, const float* __restrict__ grids_right,
+                           float* Lst, float* Rst, int C, int H, int W, int Hg, int Wg, int n) {
+  const int side = blockIdx.x / CHAIN_CLUSTER;
+  const int crank = blockIdx.x - side * CHAIN_CLUSTER;
+  const float* key = side ? next : prev;
+  const float* grids = side ? grids_right : grids_left;
+  float* st = side ? Rst : Lst;
+  const int npts = Hg * Wg;
+  const long long ls = static_cast<long long>(C) * npts;
+  for (int j = 1; j <= n - 1; ++j) {
+    const float* src = (j == 1) ? key : st + (j - 2) * ls;
+    const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
+    const long long in_plane = static_cast<long long>(Hin) * Win;
+    const float* grid = grids + static_cast<long long>(j - 1) * npts * 2;
+    float* dst = st + (j - 1) * ls;
+    for (int pt = crank * CHAIN_THREADS + threadIdx.x; pt < npts; pt += CHAIN_CLUSTER * CHAIN_THREADS) {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
+      const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, false);
+#pragma unroll 5
+      for (int c = 0; c < C; ++c) dst[c * npts + pt] = gs_fetch_cg<NM>(src + c * in_plane, t, Win);
+    }
+    if (j < n - 1) {
+      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+  }
+}
+
+// Same chain as a cooperative launch over the whole GPU: one thread per (side, grid point), grid.sync() between the
+// dependent steps.  Spreading the 2 x 8 040 points over ~63 CTAs keeps the scattered tap loads off a handful of L1s
+// (the 16-CTA cluster version is L1-throughput bound at 34 us; n-1 separate launches cost ~6 us each).
+template <class NM>
+__global__ void __launch_bounds__(256)
+block_chain_coop_kernel(const float* __restrict__ prev, const float* __restrict__ next,
+                        const float* __restrict__ grids_left, const float* __restrict__ grids_right,
+                        float* Lst, float* Rst, int C, int H, int W, int Hg, int Wg, int n) {
+  namespace cg = cooperative_groups;
+  cg::grid_group gridg = cg::this_grid();
+  const int npts = Hg * Wg;
+  const long long ls = static_cast<long long>(C) * npts;
+  const int total = 2 * npts;
+  const int nthreads = gridDim.x * blockDim.x;
+  for (int j = 1; j <= n - 1; ++j) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += nthreads) {
+      const int side = t >= npts;
+      const int pt = t - side * npts;
+      float* st = side ? Rst : Lst;
+      const float* src = (j == 1) ? (side ? next : prev) : st + (j - 2) * ls;
+      const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
+      const long long in_plane = static_cast<long long>(Hin) * Win;
+      const float* grid = (side ? grids_right : grids_left) + static_cast<long long>(j - 1) * npts * 2;
+      float* dst = st + (j - 1) * ls;
+      const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
+      const GsTap tp = gs_setup<NM>(g.x, g.y, Hin, Win, false);
+#pragma unroll 5
+      for (int c = 0; c < C; ++c) dst[c * npts + pt] = gs_fetch_cg<NM>(src + c * in_plane, tp, Win);
+    }
+    if (j < n - 1) gridg.sync();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Streaming kernel, column strips.  One thread = one output column x ROWS consecutive rows of a 128 x ROWS tile.
+// upsample_bilinear2d is separable in the order ATen evaluates it:
+//   val = h0 * (w0*a + w1*b) + h1 * (w0*c + w1*d)
+// the two inner row interpolations depend on (x, source row) only, and 16 output rows share a source row at the
+// reference's 16x ratio, so they are computed once per (map, class) and reused down the strip: ~20 tap loads per
+// pixel instead of 160, same fp32 operations in the same order (bit-identical to the per-pixel evaluation).
+// Temporal-consistency counts are fused (CT > 0): the previous frame's labels of the strip stay in registers.
+// ---------------------------------------------------------------------------
+constexpr int SROWS = 8;
+constexpr int STHREADS = 128;
+
+// torch.max semantics in 4 instructions: !(v <= best) is true for v > best or any NaN; a NaN best is never replaced.
+__device__ __forceinline__ void argmax_push(float v, int c, float& best, int& idx) {
+  const bool take = !(v <= best) && (best == best);
+  best = take ? v : best;
+  idx = take ? c : idx;
+}
+
+// LOGITS: also write the blended logits; FULLROWS: every tile has SROWS valid rows (H % SROWS == 0)
+template <class NM, int CT, bool COUNTS, bool LOGITS, bool FULLROWS>
+__global__ void __launch_bounds__(STHREADS)
+block_stream_cols_kernel(const float* __restrict__ key0, const float* __restrict__ Lst, const float* __restrict__ Rst,
+                         int Crt, int H, int W, int Hg, int Wg, int n, float sh, float sw,
+                         uint8_t* __restrict__ labels, float* __restrict__ logits,
+                         const uint8_t* __restrict__ tc_prev, unsigned long long* __restrict__ counts,
+                         int ignore_index, const BlendWeights wts) {
+  constexpr int KC = CT > 0 ? CT : 1;
+  __shared__ unsigned shc[24];
+  const int C = CT > 0 ? CT : Crt;
+  const int x = blockIdx.x * STHREADS + threadIdx.x;
+  const int y0 = blockIdx.y * SROWS;
+  const bool active = x < W;
+  const int xc = active ? x : W - 1;                       // inactive lanes compute on a valid column, store nothing
+  const long long HW = static_cast<long long>(H) * W;
+  const int lp = Hg * Wg;
+  const long long ls = static_cast<long long>(C) * lp;
+  const int rows = FULLROWS ? SROWS : min(SROWS, H - y0);
+  FieldCounts<KC> cnt;
+  if (COUNTS) cnt.init();
+
+  const UpCoord wc = up_coord<NM>(sw, xc, Wg);
+  int hi0[SROWS];
+  float hl0[SROWS], hl1[SROWS];
+#pragma unroll
+  for (int r = 0; r < SROWS; ++r) {
+    const UpCoord hc = up_coord<NM>(sh, min(y0 + r, H - 1), Hg);
+    hi0[r] = hc.i0; hl0[r] = hc.l0; hl1[r] = hc.l1;
+  }
+  int last[SROWS];
+  bool have_last = false;
+
+  // ---- frame 0: the key frame itself
+  {
+    float best[SROWS];
+    int idx[SROWS];
+#pragma unroll
+    for (int r = 0; r < SROWS; ++r) { best[r] = -INFINITY; idx[r] = 0; }
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int r = 0; r < SROWS; ++r) {
+        if (FULLROWS || r < rows) {
+          const long long o = c * HW + static_cast<long long>(y0 + r) * W + xc;
+          const float v = __ldcs(key0 + o);
+          if (LOGITS && active) __stcs(logits + o, v);
+          argmax_push(v, c, best[r], idx[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SROWS; ++r) {
+      if (FULLROWS || r < rows) {
+        const long long pix = static_cast<long long>(y0 + r) * W + xc;
+        if (labels && active) labels[pix] = static_cast<uint8_t>(idx[r]);
+        if (COUNTS) {
+          if (tc_prev != nullptr && active) {
+            const int t = __ldg(tc_prev + pix);
+            const unsigned ft = (t < KC) ? FieldCounts<KC>::field(t) : 0u;
+            const unsigned fo = (t == ignore_index) ? 0u : FieldCounts<KC>::field(idx[r]);
+            cnt.add(idx[r], fo, t, ft);
+          }
+          last[r] = idx[r];
+        }
+      }
+    }
+    have_last = true;
+  }
+  (void)have_last;
+
+  // ---- frames 1..n-1
+  int since_spill = 1;
+  for (int p = 1; p < n; ++p) {
+    const float w0 = wts.w0[p], w1 = wts.w1[p];
+    const float* Lp = Lst + (p - 1) * ls + wc.i0;
+    const float* Rp = Rst + (n - p - 1) * ls + wc.i0;
+    float best[SROWS];
+    int idx[SROWS];
+#pragma unroll
+    for (int r = 0; r < SROWS; ++r) { best[r] = -INFINITY; idx[r] = 0; }
+    for (int c = 0; c < C; ++c) {
+      const float* l = Lp + c * lp;
+      const float* rr = Rp + c * lp;
+      int cached = -1;
+      float f0 = 0.f, f1 = 0.f, b0 = 0.f, b1 = 0.f;        // inner (row) interpolations of the two source rows
+#pragma unroll
+      for (int r = 0; r < SROWS; ++r) {
+        if (FULLROWS || r < rows) {
+          if (hi0[r] != cached) {                            // block-uniform: all threads share the rows
+            cached = hi0[r];
+            const int o0 = cached * Wg, o1 = (cached + ((cached < Hg - 1) ? 1 : 0)) * Wg;
+            f0 = two_term<NM::kUpInner>(wc.l0, __ldg(l + o0), wc.l1, __ldg(l + o0 + wc.ip));
+            f1 = two_term<NM::kUpInner>(wc.l0, __ldg(l + o1), wc.l1, __ldg(l + o1 + wc.ip));
+            b0 = two_term<NM::kUpInner>(wc.l0, __ldg(rr + o0), wc.l1, __ldg(rr + o0 + wc.ip));
+            b1 = two_term<NM::kUpInner>(wc.l0, __ldg(rr + o1), wc.l1, __ldg(rr + o1 + wc.ip));
+          }
+          const float f = two_term<NM::kUpOuter>(hl0[r], f0, hl1[r], f1);
+          const float b = two_term<NM::kUpOuter>(hl0[r], b0, hl1[r], b1);
+          const float v = blend2(w0, f, w1, b);
+          if (LOGITS && active)
+            __stcs(logits + (static_cast<long long>(p) * C + c) * HW + static_cast<long long>(y0 + r) * W + xc, v);
+          argmax_push(v, c, best[r], idx[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SROWS; ++r) {
+      if (FULLROWS || r < rows) {
+        if (labels && active) labels[p * HW + static_cast<long long>(y0 + r) * W + xc] = static_cast<uint8_t>(idx[r]);
+        if (COUNTS) {
+          if (active) cnt.add(idx[r], FieldCounts<KC>::field(idx[r]), last[r], FieldCounts<KC>::field(last[r]));
+          last[r] = idx[r];
+        }
+      }
+    }
+    if (COUNTS && ++since_spill >= FieldCfg<KC>::CAP / SROWS) {
+      cnt.spill();
+      since_spill = 0;
+    }
+  }
+  if (COUNTS) cnt.finish(shc, counts, KC);
+}
+
 }  // namespace fuvs
 
 extern "C" int fuvs_upsample_bilinear_ac(const float* src, float* dst, long long planes, int Hin, int Win, int Hout,
@@ -195,29 +425,92 @@ extern "C" int fuvs_block_interval(const float* prev, const float* next, const f
     const long long ls = static_cast<long long>(C) * Hg * Wg;
     float* Lst = scratch;                    // L_1 .. L_{n-1}
     float* Rst = scratch + (n - 1) * ls;     // R_1 .. R_{n-1}
-    dim3 cgrid((Wg + 31) / 32, (Hg + 7) / 8, 2), cblock(32, 8);
-    for (int j = 1; j <= n - 1; ++j) {
-      const float* sL = (j == 1) ? prev : Lst + (j - 2) * ls;
-      const float* sR = (j == 1) ? next : Rst + (j - 2) * ls;
-      const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
-      block_chain_step_kernel<Nm><<<cgrid, cblock, 0, st>>>(
-          sL, sR, grids_left + static_cast<long long>(j - 1) * Hg * Wg * 2,
-          grids_right + static_cast<long long>(j - 1) * Hg * Wg * 2, Lst + (j - 1) * ls, Rst + (j - 1) * ls, C, Hin,
-          Win, Hg, Wg);
-      if (int e = check_launch("fuvs_block_interval(chain)")) return e;
+    // FUVS_BLOCK_CHAIN = coop (default: one cooperative launch, grid.sync between steps) | cluster (one launch, one
+    // 8-CTA cluster per side) | steps (n-1 launches)
+    static const int chain_mode = []() {
+      const char* e = getenv("FUVS_BLOCK_CHAIN");
+      return (e && e[0] == 's') ? 2 : (e && e[0] == 'c' && e[1] == 'l') ? 1 : 0;
+    }();
+    bool done = false;
+    if (chain_mode == 0) {
+      const int total = 2 * Hg * Wg;
+      int cgrid = (total + 255) / 256;
+      static int bps = blocks_per_sm(block_chain_coop_kernel<Nm>, 256);
+      const int cap = sm_count() * bps;
+      if (cgrid > cap) cgrid = cap;
+      void* args[] = {(void*)&prev, (void*)&next, (void*)&grids_left, (void*)&grids_right, (void*)&Lst, (void*)&Rst,
+                      (void*)&C, (void*)&H, (void*)&W, (void*)&Hg, (void*)&Wg, (void*)&n};
+      if (cudaLaunchCooperativeKernel((const void*)block_chain_coop_kernel<Nm>, dim3(cgrid), dim3(256), args, 0, st) ==
+          cudaSuccess) {
+        if (int e = check_launch("fuvs_block_interval(chain coop)")) return e;
+        done = true;
+      } else {
+        cudaGetLastError();   // cooperative launch unavailable: per-step launches below
+      }
+    }
+    if (done) {
+    } else if (chain_mode == 1) {
+      block_chain_cluster_kernel<Nm><<<2 * CHAIN_CLUSTER, CHAIN_THREADS, 0, st>>>(prev, next, grids_left, grids_right,
+                                                                                  Lst, Rst, C, H, W, Hg, Wg, n);
+      if (int e = check_launch("fuvs_block_interval(chain cluster)")) return e;
+    } else {
+      dim3 cgrid((Wg + 31) / 32, (Hg + 7) / 8, 2), cblock(32, 8);
+      for (int j = 1; j <= n - 1; ++j) {
+        const float* sL = (j == 1) ? prev : Lst + (j - 2) * ls;
+        const float* sR = (j == 1) ? next : Rst + (j - 2) * ls;
+        const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
+        block_chain_step_kernel<Nm><<<cgrid, cblock, 0, st>>>(
+            sL, sR, grids_left + static_cast<long long>(j - 1) * Hg * Wg * 2,
+            grids_right + static_cast<long long>(j - 1) * Hg * Wg * 2, Lst + (j - 1) * ls, Rst + (j - 1) * ls, C, Hin,
+            Win, Hg, Wg);
+        if (int e = check_launch("fuvs_block_interval(chain)")) return e;
+      }
     }
     if (labels || logits) {
       BlendWeights w;
       make_blend_weights(n, &w);
-      dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
-      if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
       const float sh = ac_scale(Hg, H), sw = ac_scale(Wg, W);
-      switch (C) {
-        case 2: block_stream_kernel<Nm, 2><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
-        case 5: block_stream_kernel<Nm, 5><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
-        default: block_stream_kernel<Nm, 0><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+      if (Hg == H && Wg == W) {
+        // sizes already match: the reference skips the interpolate call (flow/model.py:217), per-pixel kernel
+        dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+        if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
+        switch (C) {
+          case 2: block_stream_kernel<Nm, 2><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+          case 5: block_stream_kernel<Nm, 5><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+          default: block_stream_kernel<Nm, 0><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+        }
+        if (int e = check_launch("fuvs_block_interval(stream)")) return e;
+      } else {
+        dim3 grid((W + STHREADS - 1) / STHREADS, (H + SROWS - 1) / SROWS);
+        if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
+        auto cu = reinterpret_cast<unsigned long long*>(counts);
+        // counts are fused when the class count has a field-packed counter and ignore_index cannot collide with a class
+        const bool fuse = counts && labels && C <= 5 && (ignore_index < 0 || ignore_index >= C) && n * SROWS <= 4096;
+#define FUVS_COLS2(CT_, CNT_, LG_, FR_)                                                                               \
+  block_stream_cols_kernel<Nm, CT_, CNT_, LG_, FR_><<<grid, STHREADS, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, \
+                                                                               labels, logits, tc_prev, cu, ignore_index, w)
+#define FUVS_COLS(CT_, CNT_)                                            \
+  do {                                                                  \
+    if (logits) FUVS_COLS2(CT_, CNT_, true, false);                     \
+    else if (H % SROWS == 0) FUVS_COLS2(CT_, CNT_, false, true);        \
+    else FUVS_COLS2(CT_, CNT_, false, false);                           \
+  } while (0)
+        if (fuse) {
+          switch (C) {
+            case 1: FUVS_COLS(1, true); break;
+            case 2: FUVS_COLS(2, true); break;
+            case 3: FUVS_COLS(3, true); break;
+            case 4: FUVS_COLS(4, true); break;
+            default: FUVS_COLS(5, true); break;
+          }
+        } else {
+          FUVS_COLS(0, false);
+        }
+#undef FUVS_COLS
+#undef FUVS_COLS2
+        if (int e = check_launch("fuvs_block_interval(stream cols)")) return e;
+        if (fuse) return FUVS_OK;
       }
-      if (int e = check_launch("fuvs_block_interval(stream)")) return e;
     }
   }
   if (counts) return launch_temporal_counts(labels, n, HW, tc_prev, C, ignore_index, counts, st);

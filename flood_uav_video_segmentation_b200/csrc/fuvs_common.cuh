@@ -377,6 +377,59 @@ __device__ __forceinline__ void block_flush_counts(const WarpTotals<K>& tot, uns
   }
 }
 
+// ---------------------------------------------------------------------------
+// Cheaper per-thread counters for label maps whose values are known to be < K
+// (arg-max outputs): three 32-bit registers with FW-bit class fields, one shift
+// and three adds per label; spill() widens into 32-bit per-thread totals before
+// a field can overflow; finish() REDUX-reduces per warp once per kernel.
+// Requires ignore_index outside [0,K) (checked on the host).
+// ---------------------------------------------------------------------------
+template <int K> struct FieldCfg {
+  static constexpr int FW = (K <= 4) ? 8 : (K <= 5 ? 6 : 4);
+  static constexpr unsigned MASK = (1u << FW) - 1u;
+  static constexpr int CAP = static_cast<int>(MASK);     // labels a field can absorb between spills
+};
+
+template <int K>
+struct FieldCounts {
+  using FC = FieldCfg<K>;
+  unsigned accI, accO, accT;
+  unsigned totI[K], totO[K], totT[K];
+  __device__ __forceinline__ void init() {
+    accI = accO = accT = 0u;
+#pragma unroll
+    for (int c = 0; c < K; ++c) { totI[c] = 0u; totO[c] = 0u; totT[c] = 0u; }
+  }
+  __device__ __forceinline__ static unsigned field(int lab) { return 1u << (FC::FW * lab); }
+  // current label `lab` (field fo, 0 if the pixel is ignored) against the previous frame's label `last` (field flast)
+  __device__ __forceinline__ void add(int lab, unsigned fo, int last, unsigned flast) {
+    accO += fo;
+    accT += flast;
+    accI += (lab == last) ? fo : 0u;
+  }
+  __device__ __forceinline__ void spill() {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      totI[c] += (accI >> (FC::FW * c)) & FC::MASK;
+      totO[c] += (accO >> (FC::FW * c)) & FC::MASK;
+      totT[c] += (accT >> (FC::FW * c)) & FC::MASK;
+    }
+    accI = accO = accT = 0u;
+  }
+  // all threads of the block must call; sh: 24 unsigned
+  __device__ __forceinline__ void finish(unsigned* sh, unsigned long long* counts, int Kruntime) {
+    spill();
+    WarpTotals<K> wt;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      wt.I[c] = __reduce_add_sync(0xffffffffu, totI[c]);
+      wt.O[c] = __reduce_add_sync(0xffffffffu, totO[c]);
+      wt.T[c] = __reduce_add_sync(0xffffffffu, totT[c]);
+    }
+    block_flush_counts<K>(wt, sh, counts, Kruntime);
+  }
+};
+
 // Generic K <= 256: block histogram in shared memory (3*256 unsigned).
 __device__ __forceinline__ void smem_hist_add(unsigned* sh, int o, int t, int ignore, int K) {
   if (t == ignore) o = ignore;

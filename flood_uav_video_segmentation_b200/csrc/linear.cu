@@ -111,12 +111,6 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 //     adds per label), spilled to per-thread 32-bit totals before a field can
 //     overflow and REDUX-reduced once at the end of the kernel.
 // ---------------------------------------------------------------------------
-template <int K> struct FieldCfg {
-  static constexpr int FW = (K <= 4) ? 8 : (K <= 5 ? 6 : 4);
-  static constexpr unsigned MASK = (1u << FW) - 1u;
-  static constexpr int FLUSH_FRAMES = static_cast<int>(MASK) / 4;   // 4 labels per frame and thread
-};
-
 // arg-max of 4 pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
 template <int CT, bool NANSAFE>
 __device__ __forceinline__ void argmax4(const float (&x)[CT][4], int (&lab)[4]) {
@@ -136,39 +130,12 @@ __device__ __forceinline__ void argmax4(const float (&x)[CT][4], int (&lab)[4]) 
   }
 }
 
-template <int CT>
-struct LinCounts {
-  using FC = FieldCfg<CT>;
-  unsigned accI, accO, accT;
-  unsigned totI[CT], totO[CT], totT[CT];
-  __device__ __forceinline__ void init() {
-    accI = accO = accT = 0u;
-#pragma unroll
-    for (int c = 0; c < CT; ++c) { totI[c] = 0u; totO[c] = 0u; totT[c] = 0u; }
-  }
-  __device__ __forceinline__ void spill() {
-#pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      totI[c] += (accI >> (FC::FW * c)) & FC::MASK;
-      totO[c] += (accO >> (FC::FW * c)) & FC::MASK;
-      totT[c] += (accT >> (FC::FW * c)) & FC::MASK;
-    }
-    accI = accO = accT = 0u;
-  }
-  // label `lab` of the current frame against `last` (field value flast) of the previous one
-  __device__ __forceinline__ void add(int lab, unsigned fo, int last, unsigned flast) {
-    accO += fo;
-    accT += flast;
-    accI += (lab == last) ? fo : 0u;
-  }
-};
-
 template <int CT, bool COUNTS, bool NANSAFE>
 __device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&a23)[CT], const u64 (&b01)[CT],
                                               const u64 (&b23)[CT], long long HW, long long pix, int n,
                                               uint8_t* __restrict__ labels, float* __restrict__ logits,
                                               const uint8_t* __restrict__ tc_prev, int ignore_index,
-                                              const BlendWeights& wts, u64 one2, LinCounts<CT>& cnt) {
+                                              const BlendWeights& wts, u64 one2, FieldCounts<CT>& cnt) {
   using FC = FieldCfg<CT>;
   int last[4];
   unsigned flast[4];
@@ -230,7 +197,7 @@ __device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&
         last[i] = lab[i];
         flast[i] = fo;
       }
-      if (++since_spill >= FC::FLUSH_FRAMES) {
+      if (++since_spill >= FC::CAP / 4) {
         cnt.spill();
         since_spill = 0;
       }
@@ -253,7 +220,7 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
   const u64 one2 = pack2(one, one);
   const float zero = __fsub_rn(one, one);          // run-time 0 (see the note on ptxas in fuvs_common.cuh)
   const u64 zero2 = pack2(zero, zero);
-  LinCounts<CT> cnt;
+  FieldCounts<CT> cnt;
   cnt.init();
 
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
@@ -292,16 +259,7 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
     else
       linear_frames<CT, COUNTS, true>(a01, a23, b01, b23, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
   }
-  if (COUNTS) {
-    WarpTotals<CT> wt;
-#pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      wt.I[c] = __reduce_add_sync(0xffffffffu, cnt.totI[c]);
-      wt.O[c] = __reduce_add_sync(0xffffffffu, cnt.totO[c]);
-      wt.T[c] = __reduce_add_sync(0xffffffffu, cnt.totT[c]);
-    }
-    block_flush_counts<CT>(wt, sh, counts, CT);
-  }
+  if (COUNTS) cnt.finish(sh, counts, CT);
 }
 
 // Generic class count (C <= 256 when labels/counts are requested): class loop

@@ -143,6 +143,55 @@ temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, 
   else smem_hist_flush(sh, counts, K);
 }
 
+// Fast path of the temporal-consistency counts: K <= 5, ignore outside [0,K), HW % 16 == 0.  16 pixels per thread
+// (one 128-bit load per frame), field-packed counters (FieldCounts), one REDUX pass per warp at the end.
+template <int KT>
+__global__ void __launch_bounds__(256)
+temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
+                           int ignore, unsigned long long* __restrict__ counts) {
+  using FC = FieldCfg<KT>;
+  __shared__ unsigned sh[24];
+  FieldCounts<KT> cnt;
+  cnt.init();
+  const long long nvec = HW >> 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const long long pix = v << 4;
+    uint4 last = make_uint4(0u, 0u, 0u, 0u);
+    bool have_last = false;
+    if (tc_prev) {
+      last = __ldg(reinterpret_cast<const uint4*>(tc_prev + pix));
+      have_last = true;
+    }
+    int since_spill = 0;
+    for (int p = 0; p < n; ++p) {
+      const uint4 cur = __ldcs(reinterpret_cast<const uint4*>(labels + static_cast<long long>(p) * HW + pix));
+      if (have_last) {
+        const unsigned cw[4] = {cur.x, cur.y, cur.z, cur.w};
+        const unsigned lw[4] = {last.x, last.y, last.z, last.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int o = (cw[w] >> (8 * i)) & 255u, t = (lw[w] >> (8 * i)) & 255u;
+            const unsigned ft = (t < KT) ? FieldCounts<KT>::field(t) : 0u;
+            const unsigned fo = (o < KT && t != ignore) ? FieldCounts<KT>::field(o) : 0u;
+            cnt.add(o, fo, t, ft);
+          }
+        }
+        if (++since_spill >= FC::CAP / 16) {
+          cnt.spill();
+          since_spill = 0;
+        }
+      }
+      last = cur;
+      have_last = true;
+    }
+    cnt.spill();
+  }
+  cnt.finish(sh, counts, KT);
+}
+
 template <typename K>
 static int persistent_grid(K kernel, long long work_items, int threads) {
   const long long need = (work_items + threads - 1) / threads;
@@ -165,7 +214,23 @@ int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uin
     const int grid = persistent_grid(temporal_counts_kernel<V, KT_>, HW / V, threads);                  \
     temporal_counts_kernel<V, KT_><<<grid, threads, 0, st>>>(labels, n, HW, tc_prev, K, ignore_index, cu); \
   }
-  if (K <= 8) {
+  const bool v16 = (HW % 16 == 0) && aligned16(labels) && (!tc_prev || aligned16(tc_prev)) &&
+                   (ignore_index < 0 || ignore_index >= K);
+  if (v16 && K <= 5) {
+#define FUVS_TC16(KT_)                                                                                   \
+  {                                                                                                      \
+    const int grid = persistent_grid(temporal_counts_v16_kernel<KT_>, HW / 16, threads);                 \
+    temporal_counts_v16_kernel<KT_><<<grid, threads, 0, st>>>(labels, n, HW, tc_prev, ignore_index, cu); \
+  }
+    switch (K) {
+      case 1: FUVS_TC16(1) break;
+      case 2: FUVS_TC16(2) break;
+      case 3: FUVS_TC16(3) break;
+      case 4: FUVS_TC16(4) break;
+      default: FUVS_TC16(5) break;
+    }
+#undef FUVS_TC16
+  } else if (K <= 8) {
     if (vec4) FUVS_TC(4, 8) else FUVS_TC(1, 8)
   } else {
     if (vec4) FUVS_TC(4, 0) else FUVS_TC(1, 0)
