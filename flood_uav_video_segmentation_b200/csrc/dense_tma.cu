@@ -202,9 +202,11 @@ struct TmaMaps {
 };
 
 // Pipeline.  Every work item contributes C+1 "planes" to its CTA's sequence: the flow-grid tile first, then the C
-// channel windows.  NBUF shared-memory buffers cycle through the sequence; full[b] completes when the TMA bytes of
-// the plane in buffer b have landed, empty[b] when all NWARPS warps have finished reading it.  Thread 0 re-arms a
-// buffer as soon as it is empty, so loads run NBUF planes ahead and warps never meet at a block-wide barrier.
+// channel windows.  NBUF shared-memory buffers cycle through the sequence; full[b] (mbarrier) completes when the TMA
+// bytes of the plane in buffer b have landed.  A warp that has finished reading buffer b bumps done[b]; the warp
+// that arrives LAST resets the counter, re-arms full[b] and issues the TMA for the plane NBUF positions ahead.
+// Nobody ever waits for a buffer to drain (a designated producer thread that did became a convoy: every warp
+// ended up synchronised to it once per plane), and warps never meet at a block-wide barrier.
 template <class NM, int CT>
 __global__ void __launch_bounds__(THREADS, 2)
 dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
@@ -220,24 +222,24 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
   const int lane = tid & 31;
   const int tx = tid & (TW - 1), ty = tid >> 7;           // TW == 128
   const long long HW = static_cast<long long>(H) * W;
-  // bars[0..NBUF) = full, bars[NBUF..2*NBUF) = empty
+  // bars[0..NBUF) = full mbarriers; done[0..NBUF) = warps finished with the buffer
+  unsigned* done = reinterpret_cast<unsigned*>(bars + NBUF);
 
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(smem_u32(&bars[b]), 1);
-      mbar_init(smem_u32(&bars[NBUF + b]), NWARPS);
+      done[b] = 0u;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // thread 0 only: load plane q of this CTA's sequence into buffer q % NBUF
+  // one thread: load plane q of this CTA's sequence into buffer q % NBUF (the buffer is known to be drained)
   auto issue = [&](int q) {
     const int k = q / PPI, j = q - k * PPI;
     const int it = blockIdx.x + k * gridDim.x;
     if (it >= G.n_items) return;
     const int b = q % NBUF;
-    if (q >= NBUF) mbar_wait(smem_u32(&bars[NBUF + b]), static_cast<uint32_t>((q / NBUF - 1) & 1));
     const bool side = (it & 1) != 0;
     const int tile = it >> 1;
     const int tyi = tile / G.tiles_x, txi = tile - tyi * G.tiles_x;
@@ -251,11 +253,17 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
       tma_load_3d(dst, side ? &M.srcR : &M.srcL, txi * TW - HALO_X, tyi * TH - HALO_Y, j - 1, bar);
     }
   };
-  // all threads: done reading buffer b of plane q
+  // all threads: this warp is done reading the buffer of plane q; the last warp to say so refills it
   auto release = [&](int q) {
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&bars[NBUF + q % NBUF]));
-    if (tid == 0) issue(q + NBUF);
+    if (lane == 0) {
+      __threadfence_block();
+      const int b = q % NBUF;
+      if (atomicAdd(&done[b], 1u) == NWARPS - 1) {
+        done[b] = 0u;               // published to the other warps by the release-arrive on full[b] inside issue()
+        issue(q + NBUF);
+      }
+    }
   };
   if (tid == 0) {
     for (int q = 0; q < NBUF; ++q) issue(q);
@@ -422,7 +430,7 @@ int launch_ct(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cuda
   g.tiles_x = (W + TW - 1) / TW;
   g.tiles_y = (H + TH - 1) / TH;
   g.n_items = 2 * g.tiles_x * g.tiles_y;
-  int grid = 2 * sm_count();                 // two CTAs per SM: one computes while the other waits on a barrier
+  int grid = 2 * sm_count();
   if (grid > g.n_items) grid = g.n_items;
   kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, a, C, H, W, g);
   return check_launch("fuvs_dense_interval(tma step)");
