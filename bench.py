@@ -44,6 +44,15 @@ def algorithmic_bytes(mode, k=K_DELTA):
     return (5 * k - (8 if k % 2 == 0 else 7)) * S_BYTES + 2 * (k - 1) * g + (k + 1) * LB_BYTES
 
 
+def measured_traffic(mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per interval from the committed ncu launch list (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(mode)
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -54,7 +63,15 @@ def measured_peak():
 
 # ----------------------------------------------------------------------------- synthetic clips
 def make_grids(n_grids, mode, device, gen):
+    """identity + uniform(+-0.025) jitter per grid point.  mode "dense_smooth": the same jitter drawn
+    per 16x16 macro-block and bilinearly up-sampled to pixel resolution — what a dense field derived from H.264
+    motion vectors (or optical flow) looks like: spatially coherent instead of iid per pixel."""
     from flood_uav_video_segmentation_b200.synthetic import identity_grid
+    if mode == "dense_smooth":
+        base = identity_grid(H, W, "dense").to(device)
+        low = (torch.rand((n_grids, 2, H // 16 + 1, W // 16 + 1), device=device, generator=gen) - 0.5) * 0.05
+        jit = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        return (base.unsqueeze(0) + jit).contiguous()
     base = identity_grid(H, W, mode).to(device)
     jit = (torch.rand((n_grids,) + tuple(base.shape), device=device, generator=gen) - 0.5) * 0.05
     return (base.unsqueeze(0) + jit).contiguous()
@@ -77,7 +94,7 @@ def make_clip(mode, device, seed):
 def clip_bytes(mode):
     n_int = (CLIP_FRAMES - 1) // K_DELTA
     b = (n_int + 1) * S_BYTES
-    if mode == "dense":
+    if mode in ("dense", "dense_smooth"):
         b += n_int * 2 * (K_DELTA - 1) * H * W * 8
     elif mode == "block":
         b += n_int * 2 * (K_DELTA - 1) * (H // 16) * (W // 16) * 8
@@ -138,7 +155,7 @@ class ClockSampler:
 def run_interval(kernels, mode, keys, grids, it, tc_prev, counts):
     if mode == "linear":
         labels, _ = kernels.linear_blend_argmax(keys[it], keys[it + 1], K_DELTA, tc_prev=tc_prev, counts=counts)
-    elif mode == "dense":
+    elif mode in ("dense", "dense_smooth"):
         labels, _ = kernels.dense_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
                                            counts=counts, scratch=run_interval.scratch)
     else:
@@ -211,8 +228,10 @@ class _Null:
 
 # ----------------------------------------------------------------------------- end-to-end arm (host buffers)
 def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
-    """FlowBaseModel.predict_step with pinned HOST inputs: per interval H2D of both key frames and the grids on a
-    copy stream (double-buffered against compute), D2H of the uint8 label maps, counts read back at the end."""
+    """FlowBaseModel.predict_step with pinned HOST inputs.  Per interval the copy stream uploads the NEXT key frame's
+    logits and the 2(k-1) grids (the previous interval's `next` becomes this interval's `prev` on the device: each
+    key frame crosses PCIe once per clip), double-buffered against compute; the uint8 label maps go back D2H per
+    interval and the counts are read once at the end."""
     from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel
 
     class Identity(torch.nn.Module):
@@ -225,55 +244,80 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
                           backbone=Identity(), output_size=(H, W), save_video=False)
     copy_stream = torch.cuda.Stream(device)
     n_int = (CLIP_FRAMES - 1) // K_DELTA
-    slots = []
+    # key-frame ring of 4 device buffers handed out round-robin: while interval j computes on two of them the copy
+    # stream fills the one or two (clip boundary) that interval j+1 needs; a buffer is rewritten 4 uploads later, when
+    # the last interval that read it has long been enqueued (its key_free event is recorded before the wait is issued)
+    NK = 4
+    keys_dev = [torch.empty((1, C, H, W), device=device) for _ in range(NK)]
+    key_ready = [torch.cuda.Event() for _ in range(NK)]
+    key_free = [torch.cuda.Event() for _ in range(NK)]
+    gslots = []
     for _ in range(2):
-        s = {"prev": torch.empty((1, C, H, W), device=device), "next": torch.empty((1, C, H, W), device=device),
-             "ready": torch.cuda.Event(), "free": torch.cuda.Event()}
+        s = {"ready": torch.cuda.Event(), "free": torch.cuda.Event()}
         if mode != "linear":
             gshape = host_clips[0][1][0][0].shape
             s["gl"], s["gr"] = torch.empty(gshape, device=device), torch.empty(gshape, device=device)
-        slots.append(s)
+        gslots.append(s)
     out_host = [torch.empty((K_DELTA, H, W), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    h2d = 2 * S_BYTES + (0 if mode == "linear" else 2 * host_clips[0][1][0][0].numel() * 4)
+    gbytes = 0 if mode == "linear" else 2 * host_clips[0][1][0][0].numel() * 4
     d2h = K_DELTA * H * W
-    work = []   # (clip, interval)
-    ci = 0
+    state = {"ci": 0, "alloc": 0, "last_next": 0, "h2d": 0}
 
-    def stage(slot, clip, it):
+    def upload_key(host_key):
+        k = state["alloc"] % NK
+        state["alloc"] += 1
+        copy_stream.wait_event(key_free[k])
+        keys_dev[k].copy_(host_key, non_blocking=True)
+        key_ready[k].record(copy_stream)
+        state["h2d"] += S_BYTES
+        return k
+
+    def stage(j, clip, it):
+        """uploads what interval `it` of `clip` (the j-th interval of the step) needs and does not have yet"""
         keys, grids = clip
+        slot = gslots[j % 2]
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(slot["free"])
-            slot["prev"].copy_(keys[it], non_blocking=True)
-            slot["next"].copy_(keys[it + 1], non_blocking=True)
+            # first interval of a clip: both key frames; later ones: prev is the previous interval's next
+            k0 = upload_key(keys[0]) if it == 0 else state["last_next"]
+            k1 = upload_key(keys[it + 1])
             if mode != "linear":
+                copy_stream.wait_event(slot["free"])
                 slot["gl"].copy_(grids[it][0], non_blocking=True)
                 slot["gr"].copy_(grids[it][1], non_blocking=True)
-            slot["ready"].record(copy_stream)
+                slot["ready"].record(copy_stream)
+                state["h2d"] += gbytes
+        state["last_next"] = k1
+        return (k0, k1)
 
     def step():
-        nonlocal ci
         items = []
         for _ in range(clips_per_step):
-            clip = host_clips[ci % len(host_clips)]
-            ci += 1
+            clip = host_clips[state["ci"] % len(host_clips)]
+            state["ci"] += 1
             items += [(clip, it) for it in range(n_int)]
         cur = torch.cuda.current_stream(device)
-        stage(slots[0], *items[0])
+        pairs = {0: stage(0, *items[0])}
         for j, (clip, it) in enumerate(items):
-            slot = slots[j % 2]
             if j + 1 < len(items):
-                stage(slots[(j + 1) % 2], *items[j + 1])
+                pairs[j + 1] = stage(j + 1, *items[j + 1])
+            kp, kn = pairs.pop(j)
+            slot = gslots[j % 2]
             if it == 0:
                 model.last_output = None          # temporal chain resets at clip boundaries
-            cur.wait_event(slot["ready"])
+            cur.wait_event(key_ready[kp])
+            cur.wait_event(key_ready[kn])
             if mode == "linear":
                 dummy = [None] * (K_DELTA - 1)
-                batch = {"frame_prev": slot["prev"], "frame_next": slot["next"], "mvs_left": dummy, "mvs_right": dummy}
+                batch = {"frame_prev": keys_dev[kp], "frame_next": keys_dev[kn], "mvs_left": dummy, "mvs_right": dummy}
             else:
-                batch = {"frame_prev": slot["prev"], "frame_next": slot["next"],
+                cur.wait_event(slot["ready"])
+                batch = {"frame_prev": keys_dev[kp], "frame_next": keys_dev[kn],
                          "mvs_left": _GridList(slot["gl"]), "mvs_right": _GridList(slot["gr"])}
             labels = model.predict_step(batch, j)
             slot["free"].record(cur)
+            key_free[kp].record(cur)              # prev is not needed after this interval (next stays for the following one)
+            if it == n_int - 1:
+                key_free[kn].record(cur)
             out_host[j % 2].copy_(labels, non_blocking=True)          # flow/base.py:277 (already uint8)
         return len(items)
 
@@ -284,6 +328,7 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
     if world > 1:
         torch.distributed.barrier()
     model.on_predict_start()
+    state["h2d"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
@@ -300,7 +345,7 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     per_step_items = n_items // max(steps, 1)
-    return ms, h2d * per_step_items, d2h * per_step_items, res
+    return ms, state["h2d"] // max(steps, 1), d2h * per_step_items, res
 
 
 class _GridList(list):
@@ -360,7 +405,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="dense", choices=["dense", "block", "linear"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "block", "linear", "dense_smooth"])
     ap.add_argument("--clips-per-step", type=int, default=4)
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
@@ -406,15 +451,16 @@ def main():
            "clocks": sampler.summary(), "gpu_launches": int(launches),
            "output_frames_per_sec": intervals * K_DELTA * world / (ms / 1e3),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "kernel": f"fuvs_{mode}_interval",
+                        "traffic": measured_traffic(mode), "peak_source": peak_src, "kernel": f"fuvs_{mode}_interval",
                         "algorithmic_bytes_per_launch": bytes_iv,
-                        "launch": "one interval = one C-ABI call (dense: 4 dense_step_kernel + 1 temporal_counts_kernel)",
+                        "launch": "one interval = one C-ABI call (dense: 4 dense_step_tma_kernel + 1 temporal_counts_v16_kernel; "
+                                  "block: chain + stream kernel; linear: one kernel)",
                         "frac_of_nominal_8000": achieved / 8000.0},
            "miou_counts_checksum": int(counts.sum().item())}
 
     if not args.no_modes:
         modes = {}
-        for m in ("linear", "block", "dense"):
+        for m in ("linear", "block", "dense", "dense_smooth"):
             if m == mode:
                 continue
             mclips = [make_clip(m, device, 5000 + 1000 * rank + i) for i in range(args.distinct_clips)]
@@ -422,7 +468,8 @@ def main():
             miv = max(args.steps // 2, 10) * args.clips_per_step * 3
             mach = algorithmic_bytes(m) * miv / (mms / 1e3) / 1e9
             modes[m] = {"value": miv * (K_DELTA - 1) * world / (mms / 1e3), "unit": "frames/s", "achieved_gbs": mach,
-                        "frac": mach / peak, "algorithmic_bytes_per_interval": algorithmic_bytes(m)}
+                        "frac": mach / peak, "algorithmic_bytes_per_interval": algorithmic_bytes(m),
+                        "us_per_interval": mms * 1e3 / miv}
             del mclips
             torch.cuda.empty_cache()
         out["other_modes"] = modes

@@ -430,7 +430,7 @@ int launch_ct(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cuda
   g.tiles_x = (W + TW - 1) / TW;
   g.tiles_y = (H + TH - 1) / TH;
   g.n_items = 2 * g.tiles_x * g.tiles_y;
-  int grid = 2 * sm_count();
+  int grid = 2 * sm_count();                 // two CTAs per SM
   if (grid > g.n_items) grid = g.n_items;
   kern<<<grid, THREADS, SMEM_BYTES, st>>>(maps, a, C, H, W, g);
   return check_launch("fuvs_dense_interval(tma step)");

@@ -8,6 +8,8 @@
 // uint8 label maps, read the previous interval's last label map.  Each thread
 // owns VEC consecutive pixels x all C class planes: C coalesced 128-bit loads
 // per key frame, all n frames computed from registers.
+#include <cstdlib>
+
 #include "fuvs_common.cuh"
 
 namespace fuvs {
@@ -111,11 +113,11 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 //     adds per label), spilled to per-thread 32-bit totals before a field can
 //     overflow and REDUX-reduced once at the end of the kernel.
 // ---------------------------------------------------------------------------
-// arg-max of 4 pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
-template <int CT, bool NANSAFE>
-__device__ __forceinline__ void argmax4(const float (&x)[CT][4], int (&lab)[4]) {
+// arg-max of NPX pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
+template <int CT, int NPX, bool NANSAFE>
+__device__ __forceinline__ void argmaxN(const float (&x)[CT][NPX], int (&lab)[NPX]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NPX; ++i) {
     float best = x[0][i];
     int idx = 0;
 #pragma unroll
@@ -130,46 +132,72 @@ __device__ __forceinline__ void argmax4(const float (&x)[CT][4], int (&lab)[4]) 
   }
 }
 
-template <int CT, bool COUNTS, bool NANSAFE>
-__device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&a23)[CT], const u64 (&b01)[CT],
-                                              const u64 (&b23)[CT], long long HW, long long pix, int n,
-                                              uint8_t* __restrict__ labels, float* __restrict__ logits,
-                                              const uint8_t* __restrict__ tc_prev, int ignore_index,
-                                              const BlendWeights& wts, u64 one2, FieldCounts<CT>& cnt) {
+// NP pixel pairs per thread: NP = 2 -> 4 pixels (128-bit loads, 32-bit label stores),
+//                            NP = 1 -> 2 pixels (64-bit loads, 16-bit label stores; half the registers, twice the warps)
+template <int NP> struct PixIO;
+template <> struct PixIO<2> {
+  static __device__ __forceinline__ void load(const float* p, u64 (&d)[2]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    d[0] = pack2(t.x, t.y);
+    d[1] = pack2(t.z, t.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&x)[4]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+  }
+  static __device__ __forceinline__ void store_labels(uint8_t* p, const int (&l)[4]) {
+    *reinterpret_cast<unsigned*>(p) = (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
+  }
+  static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+};
+template <> struct PixIO<1> {
+  static __device__ __forceinline__ void load(const float* p, u64 (&d)[1]) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
+    d[0] = pack2(t.x, t.y);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&x)[2]) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(x[0], x[1]));
+  }
+  static __device__ __forceinline__ void store_labels(uint8_t* p, const int (&l)[2]) {
+    *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>((unsigned)l[0] | ((unsigned)l[1] << 8));
+  }
+  static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+};
+
+template <int CT, int NP, bool COUNTS, bool NANSAFE>
+__device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 (&b)[CT][NP], long long HW,
+                                              long long pix, int n, uint8_t* __restrict__ labels,
+                                              float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
+                                              int ignore_index, const BlendWeights& wts, u64 one2,
+                                              FieldCounts<CT>& cnt) {
   using FC = FieldCfg<CT>;
-  int last[4];
-  unsigned flast[4];
+  constexpr int NPX = 2 * NP;
+  int last[NPX];
   // ---- frame 0: the unblended key frame (flow/model.py:195-197)
   {
-    float x[CT][4];
+    float x[CT][NPX];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
-      unpack2(a01[c], x[c][0], x[c][1]);
-      unpack2(a23[c], x[c][2], x[c][3]);
-      if (logits) __stcs(reinterpret_cast<float4*>(logits + c * HW + pix), make_float4(x[c][0], x[c][1], x[c][2], x[c][3]));
+#pragma unroll
+      for (int h = 0; h < NP; ++h) unpack2(a[c][h], x[c][2 * h], x[c][2 * h + 1]);
+      if (logits) PixIO<NP>::store(logits + c * HW + pix, x[c]);
     }
-    int lab[4];
-    argmax4<CT, NANSAFE>(x, lab);
-    if (labels)
-      *reinterpret_cast<unsigned*>(labels + pix) =
-          (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+    int lab[NPX];
+    argmaxN<CT, NPX, NANSAFE>(x, lab);
+    if (labels) PixIO<NP>::store_labels(labels + pix, lab);
     if (COUNTS) {
       if (tc_prev != nullptr) {
-        const unsigned t = __ldg(reinterpret_cast<const unsigned*>(tc_prev + pix));
+        const unsigned t = PixIO<NP>::load_labels(tc_prev + pix);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NPX; ++i) {
           const int tl = (t >> (8 * i)) & 255u;
-          const unsigned ft = (tl < CT) ? (1u << (FC::FW * tl)) : 0u;
+          const unsigned ft = (tl < CT) ? FieldCounts<CT>::field(tl) : 0u;
           // output[target == ignore] = ignore, and ignore is outside [0,CT) on this path: nothing of this pixel counts
-          const unsigned fo = (tl == ignore_index) ? 0u : (1u << (FC::FW * lab[i]));
+          const unsigned fo = (tl == ignore_index) ? 0u : FieldCounts<CT>::field(lab[i]);
           cnt.add(lab[i], fo, tl, ft);
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        last[i] = lab[i];
-        flast[i] = 1u << (FC::FW * lab[i]);
-      }
+      for (int i = 0; i < NPX; ++i) last[i] = lab[i];
     }
   }
   // ---- frames 1..n-1: fl(fl(w0*a) + fl(w1*b))  (flow/model.py:233-237)
@@ -177,27 +205,23 @@ __device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&
   for (int p = 1; p < n; ++p) {
     const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
     float* lg = logits ? logits + (static_cast<long long>(p) * CT) * HW + pix : nullptr;
-    float x[CT][4];
+    float x[CT][NPX];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
-      unpack2(blend2x2(w0, a01[c], w1, b01[c], one2), x[c][0], x[c][1]);
-      unpack2(blend2x2(w0, a23[c], w1, b23[c], one2), x[c][2], x[c][3]);
-      if (lg) __stcs(reinterpret_cast<float4*>(lg + c * HW), make_float4(x[c][0], x[c][1], x[c][2], x[c][3]));
+#pragma unroll
+      for (int h = 0; h < NP; ++h) unpack2(blend2x2(w0, a[c][h], w1, b[c][h], one2), x[c][2 * h], x[c][2 * h + 1]);
+      if (lg) PixIO<NP>::store(lg + c * HW, x[c]);
     }
-    int lab[4];
-    argmax4<CT, NANSAFE>(x, lab);
-    if (labels)
-      *reinterpret_cast<unsigned*>(labels + static_cast<long long>(p) * HW + pix) =
-          (unsigned)lab[0] | ((unsigned)lab[1] << 8) | ((unsigned)lab[2] << 16) | ((unsigned)lab[3] << 24);
+    int lab[NPX];
+    argmaxN<CT, NPX, NANSAFE>(x, lab);
+    if (labels) PixIO<NP>::store_labels(labels + static_cast<long long>(p) * HW + pix, lab);
     if (COUNTS) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned fo = 1u << (FC::FW * lab[i]);
-        cnt.add(lab[i], fo, last[i], flast[i]);
+      for (int i = 0; i < NPX; ++i) {
+        cnt.add(lab[i], FieldCounts<CT>::field(lab[i]), last[i], FieldCounts<CT>::field(last[i]));
         last[i] = lab[i];
-        flast[i] = fo;
       }
-      if (++since_spill >= FC::CAP / 4) {
+      if (++since_spill >= FC::CAP / NPX) {
         cnt.spill();
         since_spill = 0;
       }
@@ -206,8 +230,8 @@ __device__ __forceinline__ void linear_frames(const u64 (&a01)[CT], const u64 (&
   if (COUNTS) cnt.spill();
 }
 
-template <int CT, bool COUNTS>
-__global__ void __launch_bounds__(256, 2)
+template <int CT, int NP, bool COUNTS>
+__global__ void __launch_bounds__(256, NP == 2 ? 2 : 4)
 linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __restrict__ next,
                               long long HW, int n,
                               uint8_t* __restrict__ labels, float* __restrict__ logits,
@@ -215,7 +239,8 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
                               unsigned long long* __restrict__ counts, int ignore_index,
                               const BlendWeights wts, float one) {
   __shared__ unsigned sh[24];
-  const long long nvec = HW >> 2;
+  constexpr int NPX = 2 * NP;
+  const long long nvec = HW / NPX;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const u64 one2 = pack2(one, one);
   const float zero = __fsub_rn(one, one);          // run-time 0 (see the note on ptxas in fuvs_common.cuh)
@@ -224,40 +249,36 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
   cnt.init();
 
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    const long long pix = v << 2;
-    u64 a01[CT], a23[CT], b01[CT], b23[CT];
+    const long long pix = v * NPX;
+    u64 a[CT][NP], b[CT][NP];
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      const float4 t = __ldcs(reinterpret_cast<const float4*>(prev + c * HW + pix));
-      a01[c] = pack2(t.x, t.y);
-      a23[c] = pack2(t.z, t.w);
-    }
+    for (int c = 0; c < CT; ++c) PixIO<NP>::load(prev + c * HW + pix, a[c]);
     if (n > 1) {
 #pragma unroll
-      for (int c = 0; c < CT; ++c) {
-        const float4 t = __ldcs(reinterpret_cast<const float4*>(next + c * HW + pix));
-        b01[c] = pack2(t.x, t.y);
-        b23[c] = pack2(t.z, t.w);
-      }
+      for (int c = 0; c < CT; ++c) PixIO<NP>::load(next + c * HW + pix, b[c]);
     } else {
 #pragma unroll
-      for (int c = 0; c < CT; ++c) { b01[c] = zero2; b23[c] = zero2; }
+      for (int c = 0; c < CT; ++c) {
+#pragma unroll
+        for (int h = 0; h < NP; ++h) b[c][h] = zero2;
+      }
     }
     // x*0 is 0 for finite x and NaN for Inf/NaN: one FFMA2 per pixel pair detects non-finite inputs
     u64 probe = zero2;
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
-      probe = fma2_rn(a01[c], zero2, probe);
-      probe = fma2_rn(a23[c], zero2, probe);
-      probe = fma2_rn(b01[c], zero2, probe);
-      probe = fma2_rn(b23[c], zero2, probe);
+#pragma unroll
+      for (int h = 0; h < NP; ++h) {
+        probe = fma2_rn(a[c][h], zero2, probe);
+        probe = fma2_rn(b[c][h], zero2, probe);
+      }
     }
     float pr0, pr1;
     unpack2(probe, pr0, pr1);
     if ((pr0 == pr0) && (pr1 == pr1))
-      linear_frames<CT, COUNTS, false>(a01, a23, b01, b23, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      linear_frames<CT, NP, COUNTS, false>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
     else
-      linear_frames<CT, COUNTS, true>(a01, a23, b01, b23, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      linear_frames<CT, NP, COUNTS, true>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
   }
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
@@ -322,18 +343,24 @@ linear_blend_argmax_generic_kernel(const float* __restrict__ prev, const float* 
   if (do_counts) smem_hist_flush(sh, counts, C);
 }
 
-template <int CT, bool COUNTS>
+template <int CT, int NP, bool COUNTS>
 static int launch_v4(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                      const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                      cudaStream_t st) {
   const int threads = 256;
-  const long long need = ((HW >> 2) + threads - 1) / threads;
-  static int bps = blocks_per_sm(linear_blend_argmax_v4_kernel<CT, COUNTS>, threads);
+  const long long need = ((HW / (2 * NP)) + threads - 1) / threads;
+  static int bps = blocks_per_sm(linear_blend_argmax_v4_kernel<CT, NP, COUNTS>, threads);
   const long long cap = static_cast<long long>(sm_count()) * bps;
   const int grid = static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
-  linear_blend_argmax_v4_kernel<CT, COUNTS><<<grid, threads, 0, st>>>(
+  linear_blend_argmax_v4_kernel<CT, NP, COUNTS><<<grid, threads, 0, st>>>(
       prev, next, HW, n, labels, logits, tc_prev, reinterpret_cast<unsigned long long*>(counts), ignore_index, w, 1.0f);
   return check_launch("fuvs_linear_blend_argmax");
+}
+
+// FUVS_LINEAR_PX = 2 | 4 pixels per thread (A/B switch; default chosen from measurements on the B200)
+static int linear_px() {
+  static const int v = []() { const char* e = getenv("FUVS_LINEAR_PX"); return (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : 0; }();
+  return v;
 }
 
 template <int CT, int VEC>
@@ -341,8 +368,13 @@ static int launch_fixed(const float* prev, const float* next, long long HW, int 
                         const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                         cudaStream_t st) {
   if (VEC == 4 && (ignore_index < 0 || ignore_index >= CT)) {
-    if (counts) return launch_v4<CT, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-    return launch_v4<CT, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+    const int px = linear_px() ? linear_px() : 4;
+    if (px == 4) {
+      if (counts) return launch_v4<CT, 2, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+      return launch_v4<CT, 2, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+    }
+    if (counts) return launch_v4<CT, 1, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    return launch_v4<CT, 1, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
   }
   const long long nvec = HW / VEC;
   const int threads = 256;
