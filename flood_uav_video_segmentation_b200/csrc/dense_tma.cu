@@ -113,6 +113,35 @@ __device__ __forceinline__ void plane_from_smem(const float* __restrict__ plane_
   float* dp = dst ? dst + plane_off + pix0 : nullptr;
   float* lp = (EMIT && logit_out) ? logit_out + plane_off + pix0 : nullptr;
   float* l0p = (KEY0 && logit0) ? logit0 + plane_off + pix0 : nullptr;
+  if (!EMIT && FULL) {
+    // No pointwise operand to wait for: issue all PX*4 shared-memory loads before the first FMA, so 32 independent
+    // LDS are in flight per thread (4 warps per scheduler cannot hide the conflict-stretched LDS latency otherwise).
+    float v00[PX], v01[PX], v10[PX], v11[PX];
+#pragma unroll
+    for (int r = 0; r < PX; ++r) {
+      const float* p = plane_s + T.loc[r];
+      v00[r] = p[0]; v01[r] = p[1]; v10[r] = p[BOXW]; v11[r] = p[BOXW + 1];
+    }
+    float keyv[PX];
+    if (KEY0) {
+#pragma unroll
+      for (int r = 0; r < PX; ++r) keyv[r] = plane_s[key_loc + r * (TROWS * BOXW)];
+    }
+#pragma unroll
+    for (int r = 0; r < PX; ++r) {
+      float acc = 0.f;
+      acc = tap_acc<NM>(acc, v00[r], T.wnw[r]);
+      acc = tap_acc<NM>(acc, v01[r], T.wne[r]);
+      acc = tap_acc<NM>(acc, v10[r], T.wsw[r]);
+      acc = tap_acc<NM>(acc, v11[r], T.wse[r]);
+      if (dp) dp[r * rstride] = acc;
+      if (KEY0) {
+        am[r].push(keyv[r], c);
+        if (l0p) __stcs(l0p + r * rstride, keyv[r]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < PX; ++r) {
     const float* p = plane_s + T.loc[r];
@@ -145,7 +174,6 @@ __device__ __forceinline__ void plane_from_smem(const float* __restrict__ plane_
   }
 }
 
-// Same plane with the taps gathered from global memory (item whose motion leaves the staged box).
 // Rare path: a warp whose taps leave the staged box (large motion) computes its pixels of the whole item straight
 // from global memory, exactly like the direct kernel.  Deliberately NOT inlined and fed with scalars only, so that
 // its registers do not burden the shared-memory fast path.
@@ -207,7 +235,8 @@ struct TmaMaps {
 // that arrives LAST resets the counter, re-arms full[b] and issues the TMA for the plane NBUF positions ahead.
 // Nobody ever waits for a buffer to drain (a designated producer thread that did became a convoy: every warp
 // ended up synchronised to it once per plane), and warps never meet at a block-wide barrier.
-template <class NM, int CT>
+// EMIT / KEY0 are launch-uniform (the host picks the instantiation), so each variant gets its own register budget.
+template <class NM, int CT, bool EMIT, bool KEY0>
 __global__ void __launch_bounds__(THREADS, 2)
 dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
                       TileGeom G) {
@@ -282,13 +311,13 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
     float* dst = side ? A.dstR : A.dstL;
     // the frame this side completes: side L -> frame A (other operand R_{n-j} from memory),
     //                                side R -> frame B (other operand L_{n-j} from memory)
-    const bool emit = side ? (A.emitB != 0) : (A.emitA != 0);
+    constexpr bool emit = EMIT;
     const float* point = side ? A.pointL : A.pointR;
     const float w_this = side ? A.wB1 : A.wA0;     // weight of the state computed here
     const float w_point = side ? A.wB0 : A.wA1;    // weight of the state read pointwise
     uint8_t* lab_out = side ? A.labelB : A.labelA;
     float* logit_out = side ? A.logitB : A.logitA;
-    const bool do_key0 = !side && (A.key0 != nullptr);
+    const bool do_key0 = KEY0 && !side;
 
     // ---- plane 0 of the item: the flow-grid tile -> taps of this thread's PX pixels
     ItemTaps T;
@@ -356,8 +385,8 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
       plane_from_smem<NM, EMIT_, KEY0_, false>(plane_s, T, c, plane_off, pix0, W, key_loc, dst, point, w_this, w_point, \
                                                side, logit_out, A.logit0, am);                                          \
   } while (0)
-      if (emit) FUVS_PLANE(true, false);
-      else if (do_key0) FUVS_PLANE(false, true);
+      if (EMIT) FUVS_PLANE(true, false);
+      else if (KEY0 && do_key0) FUVS_PLANE(false, true);
       else FUVS_PLANE(false, false);
 #undef FUVS_PLANE
       release(q);
@@ -415,10 +444,10 @@ bool make_grid_map(CUtensorMap* m, const float* ptr, int H, int W) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CT>
-int launch_ct(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cudaStream_t st) {
+template <int CT, bool EMIT, bool KEY0>
+int launch_variant(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = dense_step_tma_kernel<Nm, CT>;
+  auto kern = dense_step_tma_kernel<Nm, CT, EMIT, KEY0>;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_BYTES)) != cudaSuccess) {
       cudaGetLastError();
@@ -436,13 +465,20 @@ int launch_ct(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cuda
   return check_launch("fuvs_dense_interval(tma step)");
 }
 
+template <int CT>
+int launch_ct(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cudaStream_t st) {
+  if (a.emitA) return launch_variant<CT, true, false>(maps, a, C, H, W, st);
+  if (a.key0) return launch_variant<CT, false, true>(maps, a, C, H, W, st);
+  return launch_variant<CT, false, false>(maps, a, C, H, W, st);
+}
+
 }  // namespace
 
 int launch_dense_step_tma(const DenseStep& a, int C, int H, int W, cudaStream_t st) {
   // eligibility: TMA needs 16-byte aligned bases and row pitch; the even-n middle step (both operands fresh)
   // is emitted by the caller with a pointwise kernel instead
   if ((W & 3) != 0 || W < 4 || !aligned16(a.srcL) || !aligned16(a.srcR) || H >= 32768 || W >= 32768) return 1;
-  if ((a.emitA && !a.pointR) || (a.emitB && !a.pointL)) return 1;
+  if ((a.emitA && !a.pointR) || (a.emitB && !a.pointL) || (a.emitA != a.emitB)) return 1;
   if (a.key0 && (a.key0 != a.srcL || a.emitA)) return 1;   // frame 0 and a completed frame never share a side here
   if (!aligned16(a.gridL) || !aligned16(a.gridR)) return 1;
   TmaMaps maps;
