@@ -25,7 +25,7 @@ namespace fuvs {
 namespace {
 
 constexpr int TW = 128, TH = 16;            // output tile
-constexpr int TROWS = 2;                    // thread rows per CTA
+constexpr int TROWS = 4;                    // thread rows per CTA
 constexpr int PX = TH / TROWS;              // pixels per thread (one column, stride TROWS rows)
 constexpr int HALO_X = 32, HALO_Y = 16;
 constexpr int BOXW = TW + 2 * HALO_X;       // 192
@@ -54,12 +54,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken tensor map must surface as a launch error, not as a hung GPU.
+// Bounded wait: a broken tensor map must surface as a launch error, not as a hung GPU.  try_wait itself suspends the
+// warp for a hardware-defined interval, so the spin count only bounds the pathological case.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar) {
