@@ -283,6 +283,167 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
 
+// ---------------------------------------------------------------------------
+// Bulk-copy pipelined variant (HW % 4 == 0, CT <= 5).  The register-load kernel above leaves the SM idle while its
+// 16 warps wait ~1.5 us for their 10 global loads (issue slots 56 % used, DRAM 38 %: profiles/r01_ncu_linear_v2.txt).
+// Here one thread per CTA streams the 2*CT channel rows of the next 2 048-pixel tile into shared memory with
+// cp.async.bulk (UBLKCP, completion on an mbarrier) while all 512 threads compute the current tile; operands are
+// copied from shared memory to registers with 128-bit LDS and the buffer is released straight away (the last warp to
+// release re-arms it), so a tile's HBM latency is hidden behind one to two tiles of arithmetic.
+// The per-pixel arithmetic is linear_frames<> — the same code as the register-load kernel.
+// ---------------------------------------------------------------------------
+constexpr int BULK_THREADS = 512;
+constexpr int BULK_TILE = BULK_THREADS * 4;        // pixels per tile
+constexpr int BULK_STAGES = 2;
+
+__device__ __forceinline__ uint32_t lin_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ bool lin_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void lin_wait(uint32_t bar, uint32_t parity) {
+  if (lin_try_wait(bar, parity)) return;
+  unsigned spins = 0;
+  while (!lin_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();          // a fault must not hang the GPU
+  }
+}
+
+template <int CT, bool COUNTS>
+__global__ void __launch_bounds__(BULK_THREADS, 1)
+linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __restrict__ next,
+                                long long HW, int n,
+                                uint8_t* __restrict__ labels, float* __restrict__ logits,
+                                const uint8_t* __restrict__ tc_prev,
+                                unsigned long long* __restrict__ counts, int ignore_index,
+                                const BlendWeights wts, float one) {
+  extern __shared__ __align__(128) unsigned char lin_smem[];
+  __shared__ unsigned sh[24];
+  constexpr int NW = BULK_THREADS / 32;
+  const int nplanes = (n > 1) ? 2 * CT : CT;
+  float* stage_base = reinterpret_cast<float*>(lin_smem);                               // [STAGES][2*CT][BULK_TILE]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(lin_smem + static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4);
+  unsigned* done = reinterpret_cast<unsigned*>(bars + BULK_STAGES);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
+  const u64 one2 = pack2(one, one);
+  const float zero = __fsub_rn(one, one);
+  const u64 zero2 = pack2(zero, zero);
+
+  if (tid == 0) {
+    for (int s = 0; s < BULK_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lin_smem_u32(&bars[s])), "r"(1) : "memory");
+      done[s] = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // one thread: stream the channel rows of this CTA's i-th tile into stage i % STAGES
+  auto issue = [&](long long i) {
+    const long long t = blockIdx.x + i * gridDim.x;
+    if (t >= ntiles) return;
+    const int s = static_cast<int>(i % BULK_STAGES);
+    const long long pix0 = t * BULK_TILE;
+    const long long rem = HW - pix0;
+    const unsigned bytes = static_cast<unsigned>((rem < BULK_TILE ? rem : BULK_TILE) * 4);     // multiple of 16: HW % 4 == 0
+    const uint32_t bar = lin_smem_u32(&bars[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * nplanes) : "memory");
+    float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE;
+    for (int p = 0; p < nplanes; ++p) {
+      const float* g = (p < CT ? prev + p * HW : next + (p - CT) * HW) + pix0;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(lin_smem_u32(sb + static_cast<size_t>(p) * BULK_TILE)), "l"(g), "r"(bytes), "r"(bar) : "memory");
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < BULK_STAGES; ++i) issue(i);
+  }
+
+  FieldCounts<CT> cnt;
+  cnt.init();
+  for (long long i = 0;; ++i) {
+    const long long t = blockIdx.x + i * gridDim.x;
+    if (t >= ntiles) break;
+    const int s = static_cast<int>(i % BULK_STAGES);
+    lin_wait(lin_smem_u32(&bars[s]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
+    const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * 4;
+    const long long pix = t * BULK_TILE + tid * 4;
+    const bool live = pix < HW;                                  // HW % 4 == 0: a thread's 4 pixels are all in or all out
+    u64 a[CT][2], b[CT][2];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(c) * BULK_TILE);
+      a[c][0] = pack2(v.x, v.y);
+      a[c][1] = pack2(v.z, v.w);
+    }
+    if (n > 1) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(CT + c) * BULK_TILE);
+        b[c][0] = pack2(v.x, v.y);
+        b[c][1] = pack2(v.z, v.w);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) { b[c][0] = zero2; b[c][1] = zero2; }
+    }
+    // operands are in registers: hand the stage back; the last warp to do so refills it with tile i + STAGES
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&done[s], 1u) == NW - 1) {
+        done[s] = 0u;
+        issue(i + BULK_STAGES);
+      }
+    }
+    if (live) {
+      u64 probe = zero2;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        probe = fma2_rn(a[c][0], zero2, probe);
+        probe = fma2_rn(a[c][1], zero2, probe);
+        probe = fma2_rn(b[c][0], zero2, probe);
+        probe = fma2_rn(b[c][1], zero2, probe);
+      }
+      float pr0, pr1;
+      unpack2(probe, pr0, pr1);
+      if ((pr0 == pr0) && (pr1 == pr1))
+        linear_frames<CT, 2, COUNTS, false>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      else
+        linear_frames<CT, 2, COUNTS, true>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+    }
+  }
+  if (COUNTS) cnt.finish(sh, counts, CT);
+}
+
+template <int CT, bool COUNTS>
+static int launch_bulk(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
+                       const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
+                       cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + 64;
+  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return 1;                                  // caller uses the register-load kernel
+    }
+    attr_done = true;
+  }
+  const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
+  const long long cap = sm_count();
+  const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
+  kern<<<grid, BULK_THREADS, smem, st>>>(prev, next, HW, n, labels, logits, tc_prev,
+                                         reinterpret_cast<unsigned long long*>(counts), ignore_index, w, 1.0f);
+  return check_launch("fuvs_linear_blend_argmax(bulk)");
+}
+
 // Generic class count (C <= 256 when labels/counts are requested): class loop
 // inside the frame loop, key-frame values re-read through L1.
 template <int VEC>
@@ -368,6 +529,12 @@ static int launch_fixed(const float* prev, const float* next, long long HW, int 
                         const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                         cudaStream_t st) {
   if (VEC == 4 && (ignore_index < 0 || ignore_index >= CT)) {
+    static const bool want_bulk = []() { const char* e = getenv("FUVS_LINEAR_KERNEL"); return !(e && e[0] == 'r'); }();
+    if (want_bulk && CT <= 5 && HW >= 4 * BULK_TILE) {
+      const int r = counts ? launch_bulk<(CT <= 5 ? CT : 2), true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st)
+                           : launch_bulk<(CT <= 5 ? CT : 2), false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+      if (r <= 0) return r;
+    }
     const int px = linear_px() ? linear_px() : 4;
     if (px == 4) {
       if (counts) return launch_v4<CT, 2, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
