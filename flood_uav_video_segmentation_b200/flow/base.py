@@ -63,14 +63,15 @@ class FlowBaseModel(_Base):
                  no_interpolation_percentage: float = 0.0, layers: int = 101, zoom_factor: int = 8,
                  compute_metrics: bool = True, save_images: bool = False, save_video: bool = True,
                  data_root: str = "dataset/flow/", predict_v_id: str = "florida-01", pretrained: bool = True,
-                 backbone: nn.Module | None = None, output_size=(1072, 1920), **kwargs):
+                 backbone: nn.Module | None = None, output_size=(1072, 1920), reuse_keyframes: bool = True,
+                 **kwargs):
         super().__init__()
         hp = dict(classes=classes, ignore_index=ignore_index, test_h=round_train(test_h, arch),
                   test_w=round_train(test_w, arch), arch=arch, feature_based=feature_based, no_warp=no_warp,
                   no_cropping=no_cropping, no_interpolation_percentage=no_interpolation_percentage, layers=layers,
                   zoom_factor=zoom_factor, compute_metrics=compute_metrics, save_images=save_images,
                   save_video=save_video, data_root=data_root, predict_v_id=predict_v_id, pretrained=pretrained,
-                  output_size=tuple(output_size), **kwargs)
+                  output_size=tuple(output_size), reuse_keyframes=reuse_keyframes, **kwargs)
         if pl is not None:  # pragma: no cover
             self.save_hyperparameters(hp)
         else:
@@ -99,6 +100,7 @@ class FlowBaseModel(_Base):
 
     def init_model(self, backbone=None):
         self.model_G = self.get_new_model_arch_G(backbone)
+        self.model_G.reuse_keyframes = bool(self.hparams.reuse_keyframes)
 
     # ------------------------------------------------------------------ meters
     def _meter(self):
@@ -188,6 +190,7 @@ class FlowBaseModel(_Base):
         self._predict_counts = self._meter()
         self.last_output = None     # last label map of the previous interval (uint8 [H,W] on device)
         self._predict_intervals = 0
+        self.model_G.reset_keyframe_cache()
 
     @torch.no_grad()
     def predict_step(self, batch, batch_idx):
@@ -206,9 +209,11 @@ class FlowBaseModel(_Base):
             out_h, out_w = hp.output_size                      # the hard-coded (1072, 1920) of flow/base.py:275
             if (frame_prev.shape[2], frame_prev.shape[3]) == (out_h, out_w) and not self.model_G.feature_based:
                 # the resize at :275 is an identity copy -> fully fused route
+                fid = int(batch["frame_id"][0]) if "frame_id" in batch else None
                 output = self.model_G.predict_labels(
                     frame_prev, frame_next, mvs_left, mvs_right, n, prof, tc_prev=self.last_output,
-                    counts=self._predict_counts.counts if want_counts else None, ignore_index=hp.ignore_index)
+                    counts=self._predict_counts.counts if want_counts else None, ignore_index=hp.ignore_index,
+                    frame_id=fid)
             else:
                 logits = self.model_G.predict(frame_prev, frame_next, mvs_left, mvs_right, n, prof)["pred"]
                 logits = kernels.upsample_bilinear_ac(logits, (out_h, out_w))      # flow/base.py:275

@@ -69,6 +69,11 @@ class FlowModel(nn.Module):
         self.no_interpolation_percentage = no_interpolation_percentage
         # Default grid - no motion (plain attribute, not a buffer: flow/model.py:32)
         self.default_motion_vector = torch.from_numpy(get_default_grid()).float().unsqueeze(0)
+        # Key-frame reuse: in the reference every key frame goes through the network twice, as
+        # `next` of interval i and as `prev` of interval i+1 (flow/model.py:189,202).  When the caller passes frame ids
+        # the encoder/decoder output of `next` is kept for the following interval.  Plain attributes, not buffers.
+        self.reuse_keyframes = False
+        self._kf_cache = None          # (frame_id, tensor)
 
     # ------------------------------------------------------------------ forward (train / val / test)
     def forward(self, frame_current, frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index):
@@ -169,6 +174,16 @@ class FlowModel(nn.Module):
             o = _interp_ac(self.model.decoder(f), h, w)
         return o
 
+    def _cached_keyframe(self, frame_id, shape):
+        c = self._kf_cache
+        if self.reuse_keyframes and frame_id is not None and c is not None and c[0] == frame_id and \
+                tuple(c[1].shape[-2:]) == tuple(shape):
+            return c[1]
+        return None
+
+    def reset_keyframe_cache(self):
+        self._kf_cache = None
+
     def _interval_mode(self, mvs_left, h, w):
         if self.no_warp or len(mvs_left) == 0 or not _is_grid(mvs_left[0]):
             return "linear"
@@ -211,7 +226,7 @@ class FlowModel(nn.Module):
         return {"pred": logits}
 
     def predict_labels(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler, *, tc_prev=None, counts=None,
-                       ignore_index=255):
+                       ignore_index=255, frame_id=None):
         """Fused evaluation entry: predict_segmentation + max(1)[1] + uint8 cast + temporal-consistency counts
         (flow/model.py:184-241, flow/base.py:276-277, 280-295) -> uint8 [n,h,w].  Segmentation-based models only."""
         if self.feature_based:
@@ -222,8 +237,12 @@ class FlowModel(nn.Module):
             return labels
         h, w = frame_prev.shape[2], frame_prev.shape[3]
         with torch.no_grad():
-            o = self._keyframe_logits(frame_prev, h, w, profiler)
+            o = self._cached_keyframe(frame_id, (h, w))
+            if o is None:
+                o = self._keyframe_logits(frame_prev, h, w, profiler)
             o_next = self._keyframe_logits(frame_next, h, w, profiler) if frame_next is not None else None
+            if self.reuse_keyframes and frame_id is not None and o_next is not None:
+                self._kf_cache = (int(frame_id) + int(n), o_next)
             with profiler.profile("predict_warp"):
                 with profiler.profile("predict_fusion"):
                     labels, _ = self._run_interval(o, o_next, mvs_left, mvs_right, n, want_labels=True,

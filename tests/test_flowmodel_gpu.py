@@ -174,3 +174,81 @@ def test_validation_step_and_compute_metrics(cuda):
     e = mo.epoch_metrics(*tot)
     assert res["miou"] == e["miou"] and res["macc"] == e["macc"] and res["accuracy"] == e["accuracy"]
     assert epoch_metrics(*tot)["miou"] == e["miou"]
+
+
+class DeepLabParts(nn.Module):
+    """torchvision DeepLabV3 split like the reference's FlowDeepLabv3 (model/deeplabv3.py:47-54): encoder = ResNet
+    backbone -> 2048-channel stride-8 features, decoder = DeepLabHead (ASPP).  Random init, no network access."""
+
+    def __init__(self, classes=5):
+        super().__init__()
+        from torchvision.models.segmentation import deeplabv3_resnet50
+        torch.manual_seed(0)
+        m = deeplabv3_resnet50(weights=None, weights_backbone=None, aux_loss=False, num_classes=classes)
+        self.backbone = m.backbone
+        self.decoder = m.classifier
+        self.encoder = _OutOnly(self.backbone)
+
+
+class _OutOnly(nn.Module):
+    def __init__(self, m):
+        super().__init__()
+        self.m = m
+
+    def forward(self, x):
+        return self.m(x)["out"]
+
+
+@pytest.mark.parametrize("feature_based", [False, True])
+@pytest.mark.parametrize("mode", ["linear", "block"])
+def test_deeplabv3_keyframes(cuda, feature_based, mode):
+    """BASELINE.json config 3 shape class: DeepLabV3 key frames (2048-channel features at stride 8), random-init
+    weights, segmentation- and feature-based interpolation, against the oracle with the same modules."""
+    H, W, n = 193, 257, 4
+    bb = DeepLabParts().to(cuda).eval()
+    prev, nxt = (t.to(cuda) for t in frames(H, W, 5))
+    no_warp = mode == "linear"
+    if no_warp:
+        gl = gr = [torch.zeros(1, 1, device=cuda)] * (n - 1)
+    else:
+        gl = [g.to(cuda) for g in flow_grids(H, W, n, "block", clip=11, side=0)]
+        gr = [g.to(cuda) for g in flow_grids(H, W, n, "block", clip=11, side=1)]
+    fm = FlowModel(bb, feature_based=feature_based, no_warp=no_warp).eval()
+    with torch.no_grad():
+        got = fm.predict(prev, nxt, gl, gr, n, fo.NullProfiler())["pred"]
+        if feature_based:
+            ref = fo.predict_feature(bb.encoder, bb.decoder, prev, nxt, gl, gr, n, fm.default_motion_vector, no_warp)
+        else:
+            ref = fo.predict_segmentation(bb.encoder, bb.decoder, prev, nxt, gl, gr, n, no_warp)
+    assert got.shape == ref.shape == (n, 5, H, W)
+    assert bits_equal(got, ref)
+    assert torch.equal(kernels.argmax(got).long(), ref.max(1)[1])
+
+
+def test_keyframe_reuse_gives_identical_labels(cuda):
+    """Caching the `next` key frame's logits for the following interval halves the backbone
+    calls and must not change a single label or count."""
+    H, W, n, C = 96, 128, 5, 5
+    bb = TinyBackbone(classes=C).to(cuda).eval()
+    calls = {"n": 0}
+    bb.encoder.register_forward_hook(lambda *a: calls.__setitem__("n", calls["n"] + 1))
+    g = torch.Generator().manual_seed(8)
+    keys = [torch.randn(1, 3, H, W, generator=g).to(cuda) for _ in range(4)]
+    results = {}
+    for reuse in (False, True):
+        m = FlowBaseModel(classes=C, arch="pspnet", feature_based=False, no_warp=False, no_cropping=True, backbone=bb,
+                          output_size=(H, W), reuse_keyframes=reuse).to(cuda).eval()
+        m.on_predict_start()
+        calls["n"] = 0
+        outs = []
+        for it in range(3):
+            gl = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=9, interval=it, side=0)]
+            gr = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=9, interval=it, side=1)]
+            outs.append(m.predict_step({"frame_prev": keys[it], "frame_next": keys[it + 1], "mvs_left": gl,
+                                        "mvs_right": gr, "frame_id": torch.tensor([it * n])}, it).clone())
+        m.on_predict_end()
+        results[reuse] = (outs, m.intersection_meter_predict.sum.copy(), calls["n"])
+    assert results[False][2] == 6 and results[True][2] == 4
+    for a, b in zip(results[False][0], results[True][0]):
+        assert torch.equal(a, b)
+    assert np.array_equal(results[False][1], results[True][1])
