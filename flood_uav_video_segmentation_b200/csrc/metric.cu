@@ -164,8 +164,11 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
       have_last = true;
     }
     int since_spill = 0;
+    uint4 nxt = __ldcs(reinterpret_cast<const uint4*>(labels + pix));
     for (int p = 0; p < n; ++p) {
-      const uint4 cur = __ldcs(reinterpret_cast<const uint4*>(labels + static_cast<long long>(p) * HW + pix));
+      const uint4 cur = nxt;
+      if (p + 1 < n)   // software pipelining: the next frame's load is in flight while this one is counted
+        nxt = __ldcs(reinterpret_cast<const uint4*>(labels + static_cast<long long>(p + 1) * HW + pix));
       if (have_last) {
         const unsigned cw[4] = {cur.x, cur.y, cur.z, cur.w};
         const unsigned lw[4] = {last.x, last.y, last.z, last.w};
