@@ -62,14 +62,18 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------- synthetic clips
+SMOOTH_CELL = int(os.environ.get("FUVS_BENCH_SMOOTH_CELL", "120"))
+
+
 def make_grids(n_grids, mode, device, gen):
     """identity + uniform(+-0.025) jitter per grid point.  mode "dense_smooth": the same jitter drawn
-    per 16x16 macro-block and bilinearly up-sampled to pixel resolution — what a dense field derived from H.264
-    motion vectors (or optical flow) looks like: spatially coherent instead of iid per pixel."""
+    on a coarse lattice (one node per SMOOTH_CELL = 120 pixels) and bilinearly up-sampled to pixel resolution — a
+    spatially coherent field like optical flow or up-sampled H.264 motion vectors (same +-24 px amplitude, gradient
+    below 0.4 px/px) instead of iid noise per pixel."""
     from flood_uav_video_segmentation_b200.synthetic import identity_grid
     if mode == "dense_smooth":
         base = identity_grid(H, W, "dense").to(device)
-        low = (torch.rand((n_grids, 2, H // 16 + 1, W // 16 + 1), device=device, generator=gen) - 0.5) * 0.05
+        low = (torch.rand((n_grids, 2, H // SMOOTH_CELL + 1, W // SMOOTH_CELL + 1), device=device, generator=gen) - 0.5) * 0.05
         jit = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
         return (base.unsqueeze(0) + jit).contiguous()
     base = identity_grid(H, W, mode).to(device)

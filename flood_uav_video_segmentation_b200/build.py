@@ -17,13 +17,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfuvs.so")
-SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "block.cu", "pointwise.cu", "metric.cu", "calib.cu"]
+SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "dense_strip.cu", "block.cu", "pointwise.cu", "metric.cu", "calib.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v",
 ]
+if os.environ.get("FUVS_STRIP_PROF"):   # developer instrumentation of dense_strip.cu (never set for the shipped build)
+    NVCC_FLAGS.append("-DFUVS_STRIP_PROF")
 
 
 def _nvcc() -> str:

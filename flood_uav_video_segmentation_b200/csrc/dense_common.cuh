@@ -25,4 +25,7 @@ struct DenseStep {
 // negative on error.
 int launch_dense_step_tma(const DenseStep& a, int C, int H, int W, cudaStream_t st);
 
+// dense_strip.cu (column-strip sliding window, all channels resident in shared memory): same return convention.
+int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_t st);
+
 }  // namespace fuvs

@@ -264,6 +264,10 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
   }
   __syncthreads();
 
+  // Window origin of a tile, kept inside the image where the image is large enough: boxes hanging over the image
+  // edge are zero-filled by TMA but load far slower (measured in dense_strip.cu), and border clipping never reads there.
+  auto box_x = [&](int txi) { return max(0, min(txi * TW - HALO_X, W - BOXW)); };
+  auto box_y = [&](int tyi) { return tyi * TH - HALO_Y; };   // rows above / below the image: TMA zero fill, never read
   // one thread: load plane q of this CTA's sequence into buffer q % NBUF (the buffer is known to be drained)
   auto issue = [&](int q) {
     const int k = q / PPI, j = q - k * PPI;
@@ -280,7 +284,7 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
       tma_load_2d(dst, side ? &M.gridR : &M.gridL, 2 * txi * TW, tyi * TH, bar);
     } else {
       mbar_expect_tx(bar, BOX_BYTES);
-      tma_load_3d(dst, side ? &M.srcR : &M.srcL, txi * TW - HALO_X, tyi * TH - HALO_Y, j - 1, bar);
+      tma_load_3d(dst, side ? &M.srcR : &M.srcL, box_x(txi), box_y(tyi), j - 1, bar);
     }
   };
   // all threads: this warp is done reading the buffer of plane q; the last warp to say so refills it
@@ -307,7 +311,7 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
     const int tile = it >> 1;
     const int tyi = tile / G.tiles_x, txi = tile - tyi * G.tiles_x;
     const int x0 = txi * TW, y0 = tyi * TH;
-    const int xbase = x0 - HALO_X, ybase = y0 - HALO_Y;
+    const int xbase = box_x(txi), ybase = box_y(tyi);
     const int x = x0 + tx;
     float* dst = side ? A.dstR : A.dstL;
     // the frame this side completes: side L -> frame A (other operand R_{n-j} from memory),
@@ -338,7 +342,7 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
           const GsTap t = gs_setup<NM>(g.x, g.y, H, W, false);
           T.wnw[r] = t.nw; T.wne[r] = t.ne; T.wsw[r] = t.sw; T.wse[r] = t.se;
           const int lx = t.ix - xbase, ly = t.iy - ybase;
-          const bool in_box = (lx >= 0) && (lx + 1 <= BOXW - 1) && (ly >= 0) && (ly + 1 <= BOXH - 1);
+          const bool in_box = (lx >= 0) && (lx + t.dx <= BOXW - 1) && (ly >= 0) && (ly + t.dy <= BOXH - 1);
           T.loc[r] = in_box ? ly * BOXW + lx : 0;
           outside |= !in_box;
           T.valid |= 1u << r;
@@ -370,7 +374,7 @@ dense_step_tma_kernel(const __grid_constant__ TmaMaps M, const __grid_constant__
 #pragma unroll
     for (int r = 0; r < PX; ++r) am[r].init(-INFINITY);   // push(v, 0) then always selects class 0 first (also for -inf / NaN)
     const long long pix0 = static_cast<long long>(y0 + ty) * W + x;
-    const int key_loc = (HALO_Y + ty) * BOXW + HALO_X + tx;
+    const int key_loc = (HALO_Y + ty) * BOXW + (min(x, W - 1) - xbase);
 
     for (int c = 0; c < C; ++c, ++q) {
       const int b = q % NBUF;

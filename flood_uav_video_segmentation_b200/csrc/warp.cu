@@ -190,8 +190,13 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
   } else {
     BlendWeights w;
     make_blend_weights(n, &w);
-    // FUVS_DENSE_KERNEL=direct forces the L1-gather kernel (A/B measurements); default is the TMA-staged one
-    static const bool use_tma = []() { const char* e = getenv("FUVS_DENSE_KERNEL"); return !(e && e[0] == 'd'); }();
+    // FUVS_DENSE_KERNEL selects the step kernel for A/B measurements: "strip" (default: sliding-window TMA kernel,
+    // dense_strip.cu), "plane" (per-plane TMA kernel, dense_tma.cu), "direct" (L1 gather, this file).  Shapes a
+    // kernel cannot take fall through to the next one.
+    static const int kernel_sel = []() {
+      const char* e = getenv("FUVS_DENSE_KERNEL");
+      return (e && e[0] == 'd') ? 2 : (e && e[0] == 'p') ? 1 : 0;
+    }();
     float* Lst = scratch;                       // states 1..n-2
     float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
     for (int j = 1; j <= n - 1; ++j) {
@@ -223,9 +228,11 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
         a.label0 = labels;
         a.logit0 = logits;
       }
-      const int r = use_tma ? launch_dense_step_tma(a, C, H, W, st) : 1;
+      int r = 1;
+      if (kernel_sel == 0) r = launch_dense_step_strip(a, C, H, W, st);
+      if (r > 0 && kernel_sel <= 1) r = launch_dense_step_tma(a, C, H, W, st);
       if (r < 0) return r;
-      if (r > 0) {   // not eligible for the TMA-staged kernel: direct-gather kernel
+      if (r > 0) {   // not eligible for the TMA-staged kernels: direct-gather kernel
         if (int e = launch_dense_step<Nm>(a, C, H, W, st)) return e;
       }
     }

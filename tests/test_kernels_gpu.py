@@ -141,10 +141,15 @@ def test_full_size_1080p_all_modes(cuda):
             gl = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=3, side=0)]
             gr = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=3, side=1)]
             fn = kernels.block_interval if mode == "block" else kernels.dense_interval
-            labels, _ = fn(o, o_next, gl, gr, n)
+            tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
+            counts = kernels.new_counts(C, cuda)
+            labels, _ = fn(o, o_next, gl, gr, n, tc_prev=tc_prev.to(cuda), counts=counts)
         ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o, o_next, gl, gr, n, no_warp=(mode == "linear")))
         diff = int((labels.long() != ref).sum())
         assert diff == 0, f"{mode}: {diff} label pixels differ at 1080p"
+        if mode != "linear":   # counts accumulated by the interval call itself (dense: fused into the last step)
+            ref_counts, _ = oracle_temporal(ref, C, tc_prev.numpy().astype(np.int64))
+            assert np.array_equal(counts.cpu().numpy(), ref_counts), f"{mode}: temporal counts differ at 1080p"
         del ref
         torch.cuda.empty_cache()
 
