@@ -44,6 +44,10 @@ SIGNATURES = {
     "fuvs_argmax": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
     "fuvs_confusion": (_i, [_p, _i, _p, _i, _ll, _i, _i, _i, _p, _p]),
     "fuvs_temporal_counts": (_i, [_p, _i, _ll, _p, _i, _i, _p, _p]),
+    "fuvs_crop_grid_shape": (_i, [_i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fuvs_crop_grid": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "fuvs_crop_accumulate": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "fuvs_crop_finish": (_i, [_p, _p, _i, _i, _ll, _p, _p]),
     "fuvs_calib_grid_sample": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fuvs_calib_upsample": (_i, [_p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fuvs_calib_default": (_i, []),

@@ -16,8 +16,10 @@ on_predict_end.  What changes underneath:
 
 Lightning is optional: with pytorch_lightning installed the class is a LightningModule (drop-in for
 FlowLightningCLI); without it the same methods work on a plain nn.Module driven by a loop (bench.py, tests).
-The sliding-crop route (model.no_cropping=False, flow/base.py:182-234) is SURVEY.md §8f rank 3 and is not part of
-this round: it raises NotImplementedError.
+  * The sliding-crop route (model.no_cropping=False, flow/base.py:182-234) runs entirely on the device:
+    crop_motion_vector is a kernel (the reference moves every grid to the host, through numpy and cv2.resize, and
+    back: 2(k-1) round trips per crop), soft-max and the fp64 canvas update are one kernel per crop, the final
+    division and arg-max another.
 """
 from __future__ import annotations
 
@@ -27,6 +29,7 @@ from types import SimpleNamespace
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from .. import kernels
@@ -128,6 +131,68 @@ class FlowBaseModel(_Base):
         """flow/base.py:134-135."""
         return self.model_G(None, frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index)
 
+    # ------------------------------------------------------------------ sliding-crop inference
+    @staticmethod
+    def crop_windows(new_h, new_w, crop_h, crop_w, stride_rate=2 / 3):
+        """flow/base.py:183-200: the (s_h, e_h, s_w, e_w) windows in the order the reference visits them."""
+        stride_h, stride_w = int(np.ceil(crop_h * stride_rate)), int(np.ceil(crop_w * stride_rate))
+        grid_h = int(np.ceil(float(new_h - crop_h) / stride_h) + 1)
+        grid_w = int(np.ceil(float(new_w - crop_w) / stride_w) + 1)
+        for index_h in range(grid_h):
+            for index_w in range(grid_w):
+                e_h = min(index_h * stride_h + crop_h, new_h)
+                e_w = min(index_w * stride_w + crop_w, new_w)
+                yield e_h - crop_h, e_h, e_w - crop_w, e_w
+
+    @staticmethod
+    def crop_motion_vector(mvs_left, mvs_right, height, width, crop_h, crop_w, h_off, w_off):
+        """flow/transform.py:215-261 on the device (kernels.crop_grid).  Grids without a [Hg,Wg,2] shape — the [B,1]
+        dummies of no_warp clips, flow/dataset.py:200-205 — pass through unchanged (:216-221)."""
+        def has_grid(m):
+            return m is not None and isinstance(m, (list, tuple)) and len(m) > 0 and m[0].dim() >= 3
+        if not (has_grid(mvs_left) or has_grid(mvs_right)):
+            return mvs_left, mvs_right
+        crop = lambda g: kernels.crop_grid(g, height, width, crop_h, crop_w, h_off, w_off)  # noqa: E731
+        return ([crop(g) for g in mvs_left] if mvs_left is not None else None,
+                [crop(g) for g in mvs_right] if mvs_right is not None else None)
+
+    def compute_output(self, n, function, frame_prev, frame_next, mvs_left, mvs_right, *args, **kwargs):
+        """flow/base.py:182-209 -> fp64 canvas [n,classes,H,W] of class probabilities averaged over the crops.
+
+        `function` returns the crop's logits at crop size (compute_test_crop / compute_predict_crop); the soft-max of
+        flow/base.py:220,233 is fused with the canvas update.  The arg-max of the finished canvas is kept in
+        self.crop_labels (uint8 [n,H,W]) so that callers need not read the 8-byte canvas again."""
+        hp = self.hparams
+        crop_h, crop_w = hp.test_h, hp.test_w
+        _, _, new_h, new_w = frame_prev.shape
+        if crop_h > new_h or crop_w > new_w:
+            raise ValueError(f"crop {crop_h}x{crop_w} exceeds the frame {new_h}x{new_w} (the reference slices out of range)")
+        canvas = torch.zeros((n, hp.classes, new_h, new_w), dtype=torch.float64, device=frame_prev.device)
+        count = torch.zeros((new_h, new_w), dtype=torch.float64, device=frame_prev.device)
+        for s_h, e_h, s_w, e_w in self.crop_windows(new_h, new_w, crop_h, crop_w):
+            prev_c = frame_prev[:, :, s_h:e_h, s_w:e_w].clone()
+            next_c = frame_next[:, :, s_h:e_h, s_w:e_w].clone()
+            ml, mr = self.crop_motion_vector(mvs_left, mvs_right, new_h, new_w, e_h - s_h, e_w - s_w, s_h, s_w)
+            logits = function(prev_c, next_c, ml, mr, *args, **kwargs)
+            kernels.crop_accumulate(logits, canvas, count, s_h, s_w)
+        self.crop_labels = kernels.crop_finish(canvas, count)
+        return canvas
+
+    def _crop_logits(self, output, frame_prev):
+        _, _, h_i, w_i = frame_prev.shape
+        if output.shape[2] != h_i or output.shape[3] != w_i:                  # flow/base.py:217-219, 230-232
+            output = kernels.upsample_bilinear_ac(output, (h_i, w_i))
+        return output
+
+    def compute_test_crop(self, frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index):
+        """flow/base.py:213-222 without its soft-max (fused into compute_output)."""
+        return self._crop_logits(self.forward(frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index)["pred"],
+                                 frame_prev)
+
+    def compute_predict_crop(self, frame_prev, *args, **kwargs):
+        """flow/base.py:226-234 without its soft-max (fused into compute_output)."""
+        return self._crop_logits(self.model_G.predict(frame_prev, *args, **kwargs)["pred"], frame_prev)
+
     def _labels_from_forward(self, batch):
         outs = self.forward(batch["frame_prev"], batch["frame_next"], batch["mvs_left"], batch["mvs_right"],
                             batch["left_index"], batch["right_index"])
@@ -147,9 +212,13 @@ class FlowBaseModel(_Base):
         batch_test, test_idx = batch
         assert batch_test["frame_prev"].shape[0] == 1 and batch_test["label"].shape[0] == 1
         with self._profiler().profile("test_interference"):
-            if not self.hparams.no_cropping:
-                raise NotImplementedError("sliding-crop inference (no_cropping=False) is SURVEY.md §8f rank 3")
-            output = self._labels_from_forward(batch_test)
+            if not self.hparams.no_cropping:                                  # flow/base.py:163-165
+                self.compute_output(1, self.compute_test_crop, batch_test["frame_prev"], batch_test["frame_next"],
+                                    batch_test["mvs_left"], batch_test["mvs_right"], batch_test["left_index"],
+                                    batch_test["right_index"])
+                output = self.crop_labels
+            else:
+                output = self._labels_from_forward(batch_test)
         which = 1 if int(test_idx) > 0 else 0              # Texas video -> test2, Florida -> test1
         if self._test_counts[which] is None:
             self._test_counts[which] = self._meter()
@@ -204,10 +273,19 @@ class FlowBaseModel(_Base):
         prof = self._profiler()
         want_counts = bool(hp.compute_metrics)
         with prof.profile("predict_interference"):
-            if not hp.no_cropping:
-                raise NotImplementedError("sliding-crop inference (no_cropping=False) is SURVEY.md §8f rank 3")
             out_h, out_w = hp.output_size                      # the hard-coded (1072, 1920) of flow/base.py:275
-            if (frame_prev.shape[2], frame_prev.shape[3]) == (out_h, out_w) and not self.model_G.feature_based:
+            if not hp.no_cropping:                             # flow/base.py:272-273
+                canvas = self.compute_output(n, self.compute_predict_crop, frame_prev, frame_next, mvs_left, mvs_right,
+                                             n, prof)
+                if (canvas.shape[2], canvas.shape[3]) == (out_h, out_w):
+                    output = self.crop_labels                  # the resize at :275 is an identity copy
+                else:
+                    # fp64 bilinear resize of the probability canvas: a torch op, outside the accelerated path
+                    output = F.interpolate(canvas, (out_h, out_w), mode="bilinear", align_corners=True).max(1)[1].to(torch.uint8)
+                if want_counts:
+                    kernels.temporal_counts(output, hp.classes, hp.ignore_index, tc_prev=self.last_output,
+                                            counts=self._predict_counts.counts)
+            elif (frame_prev.shape[2], frame_prev.shape[3]) == (out_h, out_w) and not self.model_G.feature_based:
                 # the resize at :275 is an identity copy -> fully fused route
                 fid = int(batch["frame_id"][0]) if "frame_id" in batch else None
                 output = self.model_G.predict_labels(

@@ -238,3 +238,42 @@ def temporal_counts(labels, K, ignore_index=255, *, tc_prev=None, counts=None):
         check(load().fuvs_temporal_counts(ptr(labels), n, H * W, ptr(tc_prev), K, int(ignore_index), ptr(counts),
                                           stream_ptr(dev)))
     return counts
+
+
+def crop_grid(grid, H, W, crop_h, crop_w, h_off, w_off):
+    """fuvs_crop_grid: crop_motion_vector (flow/transform.py:215-261) for one grid [1,Hg,Wg,2] / [Hg,Wg,2] on the
+    device -> [1, crop_h//16, crop_w//16, 2]."""
+    dev = require_cuda(grid, what="crop_grid")
+    if grid.dtype != torch.float32:
+        raise FuvsError(f"crop_grid: expected a float32 grid (flow/dataset.py:240 loads them as float32), got {grid.dtype}")
+    g = grid.reshape(grid.shape[-3], grid.shape[-2], 2).contiguous()
+    out = torch.empty((1, crop_h // 16, crop_w // 16, 2), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(load().fuvs_crop_grid(ptr(g), g.shape[0], g.shape[1], int(H), int(W), int(crop_h), int(crop_w), int(h_off),
+                                    int(w_off), ptr(out), stream_ptr(dev)))
+    return out
+
+
+def crop_accumulate(logits, canvas, count, h_off, w_off):
+    """fuvs_crop_accumulate: canvas[:, :, window] += softmax(logits, 1); count[window] += 1 (flow/base.py:206-207,220,233)."""
+    dev = require_cuda(logits, canvas, count, what="crop_accumulate")
+    logits = _f32c(logits, "logits")
+    n, Cc, ch, cw = logits.shape
+    if canvas.dtype != torch.float64 or count.dtype != torch.float64 or not canvas.is_contiguous() or not count.is_contiguous():
+        raise FuvsError("crop_accumulate: canvas / count must be contiguous float64 tensors")
+    if canvas.dim() != 4 or canvas.shape[0] != n or canvas.shape[1] != Cc or tuple(count.shape) != tuple(canvas.shape[2:]):
+        raise FuvsError(f"crop_accumulate: canvas {tuple(canvas.shape)} / count {tuple(count.shape)} do not match logits {tuple(logits.shape)}")
+    H, W = canvas.shape[2:]
+    with torch.cuda.device(dev):
+        check(load().fuvs_crop_accumulate(ptr(logits), ptr(canvas), ptr(count), n, Cc, ch, cw, H, W, int(h_off), int(w_off),
+                                          stream_ptr(dev)))
+
+
+def crop_finish(canvas, count, *, want_labels=True):
+    """fuvs_crop_finish: canvas /= count in place; returns uint8 labels [n,H,W] = canvas.max(1)[1]."""
+    dev = require_cuda(canvas, count, what="crop_finish")
+    n, Cc, H, W = canvas.shape
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_labels else None
+    with torch.cuda.device(dev):
+        check(load().fuvs_crop_finish(ptr(canvas), ptr(count), n, Cc, H * W, ptr(labels), stream_ptr(dev)))
+    return labels

@@ -200,6 +200,36 @@ FUVS_API int fuvs_temporal_counts(const uint8_t* labels, int n, long long HW,
                          const uint8_t* tc_prev, int K, int ignore_index,
                          long long* counts, fuvs_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Sliding-crop inference (model.no_cropping=False) — flow/base.py:182-234.
+ *
+ * fuvs_crop_grid: crop_motion_vector for one grid (flow/transform.py:215-261,
+ * called per crop at flow/base.py:204): the blocks covered by the crop are
+ * sliced out, re-normalised to the crop's coordinate frame with numpy's
+ * float32 arithmetic and resized to [crop_h/16, crop_w/16] like
+ * cv2.resize(INTER_LINEAR).  The reference round-trips every grid through
+ * host memory for this; here it stays on the device.
+ *   grid : [Hg,Wg,2] fp32 (x,y) normalised     out : [crop_h/16, crop_w/16, 2]
+ *   H,W  : size of the frame the grid belongs to; (h_off,w_off) crop origin
+ *
+ * fuvs_crop_accumulate: canvas[:, :, h_off:h_off+crop_h, w_off:w_off+crop_w]
+ * += softmax(logits, dim=1); count[window] += 1   (flow/base.py:220,233 and
+ * 206-207).  logits [n,C,crop_h,crop_w] fp32; canvas [n,C,H,W] fp64; count
+ * [H,W] fp64, both zeroed by the caller before the first crop.
+ *
+ * fuvs_crop_finish: canvas /= count (flow/base.py:208, in place) and
+ * labels[n,HW] = canvas.max(1)[1] (flow/base.py:167,276); labels may be NULL.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_crop_grid_shape(int crop_h, int crop_w, int* out_h, int* out_w);
+FUVS_API int fuvs_crop_grid(const float* grid, int Hg, int Wg, int H, int W,
+                   int crop_h, int crop_w, int h_off, int w_off,
+                   float* out, fuvs_stream_t stream);
+FUVS_API int fuvs_crop_accumulate(const float* logits, double* canvas, double* count,
+                         int n, int C, int crop_h, int crop_w, int H, int W,
+                         int h_off, int w_off, fuvs_stream_t stream);
+FUVS_API int fuvs_crop_finish(double* canvas, const double* count, int n, int C,
+                     long long HW, uint8_t* labels, fuvs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,50 @@ def metric_cases():
     np.savez_compressed(os.path.join(OUT, "metric_cases.npz"), **rows)
 
 
+def crop_cases():
+    """crop_motion_vector (flow/transform.py:215-261, un-modified reference incl. its cv2.resize) on block and dense
+    grids, and one full sliding-crop canvas: flow/base.py:182-209 restated (flow/base.py needs Lightning, which is
+    absent) around the reference's own FlowModel.predict and crop_motion_vector."""
+    from flow.transform import crop_motion_vector as ref_cmv  # noqa: E402  (reference; imports cv2)
+    rows = {}
+    H, W = 144, 208
+    cases = [("block", 9, 13, 65, 65, 0, 0), ("block", 9, 13, 65, 65, 44, 88), ("block", 9, 13, 65, 65, 79, 143),
+             ("dense", H, W, 65, 65, 44, 88), ("block", 9, 13, 50, 84, 37, 90)]
+    for k, (mode, hg, wg, ch, cw, ho, wo) in enumerate(cases):
+        g = flow_grids(H, W, 2, mode, clip=11 + k, side=0)[0]            # [1,Hg,Wg,2] float32
+        assert tuple(g.shape[1:3]) == (hg, wg), g.shape
+        out, _ = ref_cmv([g.clone()], [g.clone()], H, W, ch, cw, ho, wo)   # CPU tensors alias their numpy view: clone
+        rows[f"c{k}_grid"], rows[f"c{k}_out"] = g.numpy(), out[0].numpy()
+        rows[f"c{k}_args"] = np.array([H, W, ch, cw, ho, wo])
+    rows["n_cases"] = np.array(len(cases))
+    # full canvas
+    n, C, ch, cw = 3, 5, 65, 65
+    bb = TinyBackbone().eval()
+    g = torch.Generator().manual_seed(21)
+    prev, nxt = torch.randn(1, 3, H, W, generator=g), torch.randn(1, 3, H, W, generator=g)
+    gl, gr = flow_grids(H, W, n, "block", clip=31, side=0), flow_grids(H, W, n, "block", clip=31, side=1)
+    m = RefFlowModel(bb, feature_based=False, no_warp=False).eval()
+    stride_h, stride_w = int(np.ceil(ch * 2 / 3)), int(np.ceil(cw * 2 / 3))
+    grid_h, grid_w = int(np.ceil(float(H - ch) / stride_h) + 1), int(np.ceil(float(W - cw) / stride_w) + 1)
+    canvas = torch.zeros((n, C, H, W), dtype=float)
+    count = torch.zeros((H, W), dtype=float)
+    with torch.no_grad():
+        for ih in range(grid_h):
+            for iw in range(grid_w):
+                e_h, e_w = min(ih * stride_h + ch, H), min(iw * stride_w + cw, W)
+                s_h, s_w = e_h - ch, e_w - cw
+                ml, mr = ref_cmv([x.clone() for x in gl], [x.clone() for x in gr], H, W, ch, cw, s_h, s_w)
+                out = m.predict(prev[:, :, s_h:e_h, s_w:e_w].clone(), nxt[:, :, s_h:e_h, s_w:e_w].clone(), ml, mr, n, Prof())["pred"]
+                count[s_h:e_h, s_w:e_w] += 1
+                canvas[:, :, s_h:e_h, s_w:e_w] += torch.nn.functional.softmax(out, dim=1)
+    canvas /= count.unsqueeze(0).unsqueeze(0)
+    rows.update(full_prev=prev.numpy(), full_next=nxt.numpy(), full_gl=np.stack([x.numpy() for x in gl]),
+                full_gr=np.stack([x.numpy() for x in gr]), full_canvas_sub=canvas[:, :, ::3, ::3].numpy(),
+                full_labels=canvas.max(1)[1].numpy().astype(np.uint8), full_crop=np.array([ch, cw, grid_h * grid_w]))
+    np.savez_compressed(os.path.join(OUT, "crop_cases.npz"), **rows)
+    print("crop cases", len(cases), "canvas", tuple(canvas.shape), "crops", grid_h * grid_w)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)        # fixtures must not depend on the thread count
@@ -142,8 +186,13 @@ def main():
     forward_case("forward_feat_warp", True, False)
     forward_case("forward_feat_nowarp", True, True)
     metric_cases()
+    crop_cases()
     np.savez_compressed(os.path.join(OUT, "default_grid.npz"), grid=ref_default_grid())
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "crop":      # regenerate only the crop fixtures
+        torch.set_num_threads(1)
+        crop_cases()
+    else:
+        main()
