@@ -457,8 +457,9 @@ def main():
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": measured_traffic(mode), "peak_source": peak_src, "kernel": f"fuvs_{mode}_interval",
                         "algorithmic_bytes_per_launch": bytes_iv,
-                        "launch": "one interval = one C-ABI call (dense: 4 dense_step_tma_kernel + 1 temporal_counts_v16_kernel; "
-                                  "block: chain + stream kernel; linear: one kernel)",
+                        "launch": "one interval = one C-ABI call (dense: 4 dense_strip_kernel steps + 1 temporal_counts_v16_kernel; "
+                                  "block: chain + stream kernel; linear: one kernel); duration = CUDA events over the "
+                                  "timed region / intervals",
                         "frac_of_nominal_8000": achieved / 8000.0},
            "miou_counts_checksum": int(counts.sum().item())}
 
@@ -491,7 +492,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu:
         hc = host_clips[0] if host_clips else to_host_clip(clips[0])
-        n_samp = 3
+        n_samp = 30 if mode in ("dense", "dense_smooth") else 45   # ~10-15 s of host work on the box's cores
         dt, lab_cpu = time_cpu(mode, ([k.clone() for k in hc[0]], hc[1]), n_samp)
         # same interval on the GPU for an informational label comparison (near-ties may differ: torch-CPU != torch-CUDA)
         lab_gpu = run_interval(kernels, mode, clips[0][0], clips[0][1], (n_samp - 1) % 3, None, None)

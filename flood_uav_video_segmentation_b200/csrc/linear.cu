@@ -114,6 +114,18 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 //     overflow and REDUX-reduced once at the end of the kernel.
 // ---------------------------------------------------------------------------
 // arg-max of NPX pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
+// One arg-max step as compare + two PREDICATED MOVES.  Written in PTX because nvcc turns `take ? v : best` into
+// FSEL/SEL, which share the half-rate ALU pipe with the FSETP compares (the kernel was ALU-pipe bound: 75 of 156
+// instructions per frame, profiles/r01_ncu_linear_v3_bulk.txt); predicated moves can issue on the FMA pipe.
+__device__ __forceinline__ void argmax_step(float& best, int& idx, float v, int c) {
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f32 p, %2, %0;\n\t"
+      "@p mov.f32 %0, %2;\n\t"
+      "@p mov.s32 %1, %3;\n\t}"
+      : "+f"(best), "+r"(idx)
+      : "f"(v), "r"(c));
+}
+
 template <int CT, int NPX, bool NANSAFE>
 __device__ __forceinline__ void argmaxN(const float (&x)[CT][NPX], int (&lab)[NPX]) {
 #pragma unroll
@@ -123,10 +135,13 @@ __device__ __forceinline__ void argmaxN(const float (&x)[CT][NPX], int (&lab)[NP
 #pragma unroll
     for (int c = 1; c < CT; ++c) {
       const float v = x[c][i];
-      bool take = v > best;
-      if (NANSAFE) take = take || ((v != v) && (best == best));
-      best = take ? v : best;
-      idx = take ? c : idx;
+      if (NANSAFE) {
+        const bool take = (v > best) || ((v != v) && (best == best));
+        best = take ? v : best;
+        idx = take ? c : idx;
+      } else {
+        argmax_step(best, idx, v, c);
+      }
     }
     lab[i] = idx;
   }
@@ -163,7 +178,7 @@ template <> struct PixIO<1> {
   static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
 };
 
-template <int CT, int NP, bool COUNTS, bool NANSAFE>
+template <int CT, int NP, bool COUNTS, bool NANSAFE, bool LOGITS = true>
 __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 (&b)[CT][NP], long long HW,
                                               long long pix, int n, uint8_t* __restrict__ labels,
                                               float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
@@ -179,7 +194,7 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
     for (int c = 0; c < CT; ++c) {
 #pragma unroll
       for (int h = 0; h < NP; ++h) unpack2(a[c][h], x[c][2 * h], x[c][2 * h + 1]);
-      if (logits) PixIO<NP>::store(logits + c * HW + pix, x[c]);
+      if (LOGITS && logits) PixIO<NP>::store(logits + c * HW + pix, x[c]);
     }
     int lab[NPX];
     argmaxN<CT, NPX, NANSAFE>(x, lab);
@@ -204,13 +219,13 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
   int since_spill = 1;
   for (int p = 1; p < n; ++p) {
     const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
-    float* lg = logits ? logits + (static_cast<long long>(p) * CT) * HW + pix : nullptr;
+    float* lg = (LOGITS && logits) ? logits + (static_cast<long long>(p) * CT) * HW + pix : nullptr;
     float x[CT][NPX];
 #pragma unroll
     for (int c = 0; c < CT; ++c) {
 #pragma unroll
       for (int h = 0; h < NP; ++h) unpack2(blend2x2(w0, a[c][h], w1, b[c][h], one2), x[c][2 * h], x[c][2 * h + 1]);
-      if (lg) PixIO<NP>::store(lg + c * HW, x[c]);
+      if (LOGITS && lg) PixIO<NP>::store(lg + c * HW, x[c]);
     }
     int lab[NPX];
     argmaxN<CT, NPX, NANSAFE>(x, lab);
@@ -314,7 +329,7 @@ __device__ __forceinline__ void lin_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int CT, bool COUNTS>
+template <int CT, bool COUNTS, bool LOGITS>
 __global__ void __launch_bounds__(BULK_THREADS, 1)
 linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __restrict__ next,
                                 long long HW, int n,
@@ -414,20 +429,20 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
       float pr0, pr1;
       unpack2(probe, pr0, pr1);
       if ((pr0 == pr0) && (pr1 == pr1))
-        linear_frames<CT, 2, COUNTS, false>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+        linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
       else
-        linear_frames<CT, 2, COUNTS, true>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+        linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
     }
   }
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
 
-template <int CT, bool COUNTS>
+template <int CT, bool COUNTS, bool LOGITS>
 static int launch_bulk(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                        const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                        cudaStream_t st) {
   const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + 64;
-  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS>;
+  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS>;
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
@@ -531,8 +546,14 @@ static int launch_fixed(const float* prev, const float* next, long long HW, int 
   if (VEC == 4 && (ignore_index < 0 || ignore_index >= CT)) {
     static const bool want_bulk = []() { const char* e = getenv("FUVS_LINEAR_KERNEL"); return !(e && e[0] == 'r'); }();
     if (want_bulk && CT <= 5 && HW >= 4 * BULK_TILE) {
-      const int r = counts ? launch_bulk<(CT <= 5 ? CT : 2), true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st)
-                           : launch_bulk<(CT <= 5 ? CT : 2), false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+      constexpr int CB = CT <= 5 ? CT : 2;
+      int r;
+      if (logits)
+        r = counts ? launch_bulk<CB, true, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st)
+                   : launch_bulk<CB, false, true>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+      else
+        r = counts ? launch_bulk<CB, true, false>(prev, next, HW, n, labels, nullptr, tc_prev, counts, ignore_index, w, st)
+                   : launch_bulk<CB, false, false>(prev, next, HW, n, labels, nullptr, nullptr, nullptr, ignore_index, w, st);
       if (r <= 0) return r;
     }
     const int px = linear_px() ? linear_px() : 4;
