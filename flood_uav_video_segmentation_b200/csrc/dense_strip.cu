@@ -157,12 +157,17 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 #else
   constexpr int dbg0 = 0;
 #endif
+  // Programmatic dependent launch: this CTA may have been scheduled while the previous kernel of the stream (the
+  // step that produced our source states) is still draining.  Let our own successor do the same, set up the
+  // barriers, then wait for the predecessor's memory to be complete before the first global access.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int b = 0; b < MAX_SLOTS; ++b) mbar_init(bar0 + 8u * b, 1);
     for (int b = 0; b < 4; ++b) done[b] = 0u;
     fence_barrier_init();
   }
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Left edge of a strip's window.  Kept inside the image where the image is wide enough: a box that hangs over
   // the image edge is zero-filled by TMA but loads far slower (measured: the CTAs of the last strip waited 50k
@@ -222,12 +227,31 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     const int rstride = TROWS * W;
     const bool vx = x < W;
 
-    float2 g[PX];
+    // Flow vectors are prefetched TWO blocks ahead and the pointwise operand of emitting steps ONE block ahead: a
+    // block takes ~2.5k cycles, less than a loaded HBM round trip (with one block of prefetch the first use of the
+    // vector was the top stall of the kernel, profiles/r01_ncu_dense_strip_smooth.txt).
+    auto load_grid = [&](int yb, bool on, float2 (&dstg)[PX]) {
 #pragma unroll
-    for (int r = 0; r < PX; ++r) {
-      const int y = j0 * RB + ty + r * TROWS;
-      g[r] = (vx && y < H && !(dbg0 & 16)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
-    }
+      for (int r = 0; r < PX; ++r) {
+        const int y = yb + ty + r * TROWS;
+        dstg[r] = (on && vx && y < H && !(dbg0 & 16)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
+      }
+    };
+    auto load_other = [&](int yb, bool on, float (&dsto)[PX][CR]) {
+      if (!(EMIT && CT > 0)) return;
+#pragma unroll
+      for (int r = 0; r < PX; ++r) {
+        const int y = yb + ty + r * TROWS;
+        const bool live = on && vx && y < H;
+#pragma unroll
+        for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldg(point + (c * HWi + y * W + x)) : 0.f;
+      }
+    };
+    float2 g[PX], g1[PX];
+    float other[PX][CR];
+    load_grid(j0 * RB, true, g);
+    load_grid(j0 * RB + RB, nb > 1, g1);
+    load_other(j0 * RB, true, other);
     // ring position of the window's top slot (slot load sb + jj): buffer b0, phase parity q0
     int b0 = sb % NS;
     unsigned q0 = static_cast<unsigned>(sb / NS) & 1u;
@@ -265,21 +289,11 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         if (t.dx) T.dxm |= 1u << r;
         if (t.dy) T.dym |= 1u << r;
       }
-      // ---- global operands that do not depend on the ring: issue before waiting for it
-      float other[PX][CR];
-      if (EMIT && CT > 0) {
-#pragma unroll
-        for (int r = 0; r < PX; ++r)
-#pragma unroll
-          for (int c = 0; c < CR; ++c)
-            other[r][c] = ((T.valid >> r) & 1u) ? __ldg(point + (c * HWi + pix0 + r * rstride)) : 0.f;
-      }
-      float2 gn[PX];
-#pragma unroll
-      for (int r = 0; r < PX; ++r) {
-        const int y = y0 + RB + ty + r * TROWS;
-        gn[r] = (jj + 1 < nb && vx && y < H && !(dbg0 & 16)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
-      }
+      // ---- prefetches for the following blocks (registers only; nothing here depends on the ring)
+      float2 g2[PX];
+      float other_next[PX][CR];
+      load_grid(y0 + 2 * RB, jj + 2 < nb, g2);
+      load_other(y0 + RB, jj + 1 < nb, other_next);
       const bool use_global = __any_sync(0xffffffffu, outm != 0u);
 
       // ---- the ring slots of this block's window: the newest one, and all of them at the start of a segment
@@ -377,7 +391,12 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
       released = rel_after;
 
 #pragma unroll
-      for (int r = 0; r < PX; ++r) g[r] = gn[r];
+      for (int r = 0; r < PX; ++r) {
+        g[r] = g1[r];
+        g1[r] = g2[r];
+#pragma unroll
+        for (int c = 0; c < CR; ++c) other[r][c] = other_next[r][c];
+      }
       if (++b0 == NS) { b0 = 0; q0 ^= 1u; }
     }
     sb += nb + WIN - 1;
@@ -416,7 +435,18 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.wr = 4;
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
-  kern<<<grid, TW * TROWS, smem, st>>>(maps, a, C, H, W, g);
+  static const bool pdl = []() { const char* e = getenv("FUVS_STRIP_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TW * TROWS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (cudaLaunchKernelEx(&cfg, kern, maps, a, C, H, W, g) != cudaSuccess) return check_launch("fuvs_dense_interval(strip step)");
   return check_launch("fuvs_dense_interval(strip step)");
 }
 

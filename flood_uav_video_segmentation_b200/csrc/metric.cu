@@ -151,6 +151,10 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
                            int ignore, unsigned long long* __restrict__ counts) {
   using FC = FieldCfg<KT>;
   __shared__ unsigned sh[24];
+  // programmatic dependent launch (see dense_strip.cu): start while the producer of the label maps drains, let the
+  // next kernel of the stream do the same, touch memory only after the producer has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   FieldCounts<KT> cnt;
   cnt.init();
   const long long nvec = HW >> 4;
@@ -223,7 +227,16 @@ int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uin
 #define FUVS_TC16(KT_)                                                                                   \
   {                                                                                                      \
     const int grid = persistent_grid(temporal_counts_v16_kernel<KT_>, HW / 16, threads);                 \
-    temporal_counts_v16_kernel<KT_><<<grid, threads, 0, st>>>(labels, n, HW, tc_prev, ignore_index, cu); \
+    cudaLaunchConfig_t cfg = {};                                                                         \
+    cfg.gridDim = dim3(grid);                                                                            \
+    cfg.blockDim = dim3(threads);                                                                        \
+    cfg.stream = st;                                                                                     \
+    cudaLaunchAttribute attr[1];                                                                         \
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                     \
+    attr[0].val.programmaticStreamSerializationAllowed = 1;                                              \
+    cfg.attrs = attr;                                                                                    \
+    cfg.numAttrs = 1;                                                                                    \
+    cudaLaunchKernelEx(&cfg, temporal_counts_v16_kernel<KT_>, labels, n, HW, tc_prev, ignore_index, cu); \
   }
     switch (K) {
       case 1: FUVS_TC16(1) break;
