@@ -37,6 +37,8 @@ def algorithmic_bytes(mode, k=K_DELTA):
     """algorithmic HBM bytes per interval (uint8 labels)."""
     if mode == "linear":
         return 2 * S_BYTES + k * LB_BYTES + LB_BYTES
+    if mode == "linear_lowres":    # key frames read at decoder resolution (stride 8), SURVEY.md §8f rank 1
+        return 2 * C * (H // 8) * (W // 8) * 4 + k * LB_BYTES + LB_BYTES
     if mode == "block":
         hg, wg = H // 16, W // 16
         return S_BYTES + 8 * C * hg * wg * 4 + 2 * (k - 1) * hg * wg * 8 + (k + 1) * LB_BYTES
@@ -85,10 +87,11 @@ def make_clip(mode, device, seed):
     """One 16-frame clip: 4 key-frame logit maps [1,C,H,W] and, per interval, stacked grids [k-1,Hg,Wg,2] x2."""
     gen = torch.Generator(device=device).manual_seed(seed)
     n_int = (CLIP_FRAMES - 1) // K_DELTA
-    keys = [torch.randn((1, C, H, W), device=device, generator=gen) for _ in range(n_int + 1)]
+    kh, kw = (H // 8, W // 8) if mode == "linear_lowres" else (H, W)
+    keys = [torch.randn((1, C, kh, kw), device=device, generator=gen) for _ in range(n_int + 1)]
     grids = []
     for _ in range(n_int):
-        if mode == "linear":
+        if mode in ("linear", "linear_lowres"):
             grids.append((None, None))
         else:
             grids.append((make_grids(K_DELTA - 1, mode, device, gen), make_grids(K_DELTA - 1, mode, device, gen)))
@@ -159,6 +162,8 @@ class ClockSampler:
 def run_interval(kernels, mode, keys, grids, it, tc_prev, counts):
     if mode == "linear":
         labels, _ = kernels.linear_blend_argmax(keys[it], keys[it + 1], K_DELTA, tc_prev=tc_prev, counts=counts)
+    elif mode == "linear_lowres":
+        labels, _ = kernels.linear_lowres_blend_argmax(keys[it], keys[it + 1], (H, W), K_DELTA, tc_prev=tc_prev, counts=counts)
     elif mode in ("dense", "dense_smooth"):
         labels, _ = kernels.dense_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
                                            counts=counts, scratch=run_interval.scratch)
@@ -409,7 +414,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="dense", choices=["dense", "block", "linear", "dense_smooth"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "block", "linear", "dense_smooth", "linear_lowres"])
     ap.add_argument("--clips-per-step", type=int, default=4)
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
@@ -465,7 +470,7 @@ def main():
 
     if not args.no_modes:
         modes = {}
-        for m in ("linear", "block", "dense", "dense_smooth"):
+        for m in ("linear", "linear_lowres", "block", "dense", "dense_smooth"):
             if m == mode:
                 continue
             mclips = [make_clip(m, device, 5000 + 1000 * rank + i) for i in range(args.distinct_clips)]

@@ -34,6 +34,8 @@ SIGNATURES = {
     "fuvs_launch_count": (_ll, []),
     "fuvs_device_ok": (_i, []),
     "fuvs_linear_blend_argmax": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "fuvs_linear_lowres_supported": (_i, [_i, _i, _i]),
+    "fuvs_linear_lowres_blend_argmax": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "fuvs_warp_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fuvs_dense_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_dense_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),

@@ -459,6 +459,139 @@ static int launch_bulk(const float* prev, const float* next, long long HW, int n
   return check_launch("fuvs_linear_blend_argmax(bulk)");
 }
 
+// ---------------------------------------------------------------------------
+// Key frames given at DECODER resolution.  The reference up-samples the decoder output to
+// the frame size (F.interpolate(bilinear, align_corners=True), flow/model.py:191-193,205-206) before anything else;
+// that writes 2*S to HBM per interval and the blend reads it back.  Here the up-sample is evaluated on the fly with
+// the op order kept (up-sample, THEN blend): a CTA owns one source-row interval i0 (the output rows whose floor source
+// row is i0 — 8 rows at the usual stride-8 decoders), computes the horizontal interpolations of source rows i0 and
+// i0+1 once into shared memory ([2 key frames][2 rows][C][W] floats), and every output row is then one vertical
+// two-term per value followed by linear_frames<> — the same per-pixel code as the full-resolution kernels.
+// ---------------------------------------------------------------------------
+constexpr int LR_THREADS = 256;      // two CTAs per SM: one CTA's phase 1 overlaps the other's phase 2
+
+template <int CT, bool COUNTS, bool LOGITS>
+__global__ void __launch_bounds__(LR_THREADS, 2)
+linear_lowres_kernel(const float* __restrict__ prev_lr, const float* __restrict__ next_lr, int hl, int wl, int H, int W,
+                     int n, float sh, float sw, int XW, int nchunks,
+                     uint8_t* __restrict__ labels, float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
+                     unsigned long long* __restrict__ counts, int ignore_index, const BlendWeights wts, float one) {
+  extern __shared__ __align__(16) float lr_hs[];            // [kf][row][c][XW]
+  __shared__ unsigned sh24[24];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x / nchunks, chunk = blockIdx.x - i0 * nchunks;
+  const int x0 = chunk * XW;
+  const int xw = min(XW, W - x0);
+  const long long HW = static_cast<long long>(H) * W;
+  const int lplane = hl * wl;
+  const u64 one2 = pack2(one, one);
+  const float zero = __fsub_rn(one, one);
+  const u64 zero2 = pack2(zero, zero);
+  FieldCounts<CT> cnt;
+  cnt.init();
+
+  // output rows of this interval: floor(sh * y) == i0, with the float arithmetic of up_coord()
+  auto src_row = [&](int y) { return static_cast<int>(__fmul_rn(sh, static_cast<float>(y))); };
+  int y_lo = (sh > 0.f) ? static_cast<int>(static_cast<float>(i0) / sh) : 0;
+  y_lo = max(0, min(y_lo, H - 1));
+  while (y_lo > 0 && src_row(y_lo - 1) >= i0) --y_lo;
+  while (y_lo < H && src_row(y_lo) < i0) ++y_lo;
+  int y_hi = y_lo;
+  while (y_hi < H && src_row(y_hi) == i0) ++y_hi;
+
+  if (y_hi > y_lo) {
+    // ---- phase 1: horizontal two-terms of source rows i0 and i0 + ip (UpSample.cuh: w0*a + w1*b)
+    const int ip_h = (i0 < hl - 1) ? 1 : 0;
+    const int nkf = (n > 1) ? 2 : 1;
+    for (int xx = tid; xx < xw; xx += LR_THREADS) {
+      const UpCoord wc = up_coord<Nm>(sw, x0 + xx, wl);
+      const int o0 = i0 * wl + wc.i0, o1 = (i0 + ip_h) * wl + wc.i0;
+#pragma unroll
+      for (int kf = 0; kf < 2; ++kf) {
+        if (kf < nkf) {
+          const float* src = kf ? next_lr : prev_lr;
+#pragma unroll
+          for (int c = 0; c < CT; ++c) {
+            const float* pl = src + c * lplane;
+            lr_hs[((kf * 2 + 0) * CT + c) * XW + xx] = two_term<Nm::kUpInner>(wc.l0, __ldg(pl + o0), wc.l1, __ldg(pl + o0 + wc.ip));
+            lr_hs[((kf * 2 + 1) * CT + c) * XW + xx] = two_term<Nm::kUpInner>(wc.l0, __ldg(pl + o1), wc.l1, __ldg(pl + o1 + wc.ip));
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: vertical two-term, blends, arg-max, counts
+    for (int y = y_lo; y < y_hi; ++y) {
+      const UpCoord hc = up_coord<Nm>(sh, y, hl);
+      for (int xx = tid * 4; xx < xw; xx += LR_THREADS * 4) {
+        u64 a[CT][2], b[CT][2];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const float4 r0 = *reinterpret_cast<const float4*>(lr_hs + ((0 * 2 + 0) * CT + c) * XW + xx);
+          const float4 r1 = *reinterpret_cast<const float4*>(lr_hs + ((0 * 2 + 1) * CT + c) * XW + xx);
+          a[c][0] = pack2(two_term<Nm::kUpOuter>(hc.l0, r0.x, hc.l1, r1.x), two_term<Nm::kUpOuter>(hc.l0, r0.y, hc.l1, r1.y));
+          a[c][1] = pack2(two_term<Nm::kUpOuter>(hc.l0, r0.z, hc.l1, r1.z), two_term<Nm::kUpOuter>(hc.l0, r0.w, hc.l1, r1.w));
+          if (n > 1) {
+            const float4 s0 = *reinterpret_cast<const float4*>(lr_hs + ((1 * 2 + 0) * CT + c) * XW + xx);
+            const float4 s1 = *reinterpret_cast<const float4*>(lr_hs + ((1 * 2 + 1) * CT + c) * XW + xx);
+            b[c][0] = pack2(two_term<Nm::kUpOuter>(hc.l0, s0.x, hc.l1, s1.x), two_term<Nm::kUpOuter>(hc.l0, s0.y, hc.l1, s1.y));
+            b[c][1] = pack2(two_term<Nm::kUpOuter>(hc.l0, s0.z, hc.l1, s1.z), two_term<Nm::kUpOuter>(hc.l0, s0.w, hc.l1, s1.w));
+          } else {
+            b[c][0] = zero2;
+            b[c][1] = zero2;
+          }
+        }
+        u64 probe = zero2;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          probe = fma2_rn(a[c][0], zero2, probe);
+          probe = fma2_rn(a[c][1], zero2, probe);
+          probe = fma2_rn(b[c][0], zero2, probe);
+          probe = fma2_rn(b[c][1], zero2, probe);
+        }
+        float pr0, pr1;
+        unpack2(probe, pr0, pr1);
+        const long long pix = static_cast<long long>(y) * W + x0 + xx;
+        if ((pr0 == pr0) && (pr1 == pr1))
+          linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+        else
+          linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      }
+    }
+  }
+  if (COUNTS) cnt.finish(sh24, counts, CT);
+}
+
+static inline float lr_scale(int in_size, int out_size) {
+  return out_size > 1 ? static_cast<float>(in_size - 1) / (out_size - 1) : 0.f;   // area_pixel_compute_scale, align_corners
+}
+
+template <int CT>
+static int launch_lowres(const float* prev_lr, const float* next_lr, int hl, int wl, int H, int W, int n, uint8_t* labels,
+                         float* logits, const uint8_t* tc_prev, long long* counts, int ignore_index,
+                         const BlendWeights& w, cudaStream_t st) {
+  const int budget_floats = (108 * 1024) / 4;      // two CTAs per SM
+  int nchunks = 1;
+  while (4ll * CT * (((W + nchunks - 1) / nchunks + 3) & ~3) > budget_floats) ++nchunks;
+  const int XW = ((W + nchunks - 1) / nchunks + 3) & ~3;
+  const size_t smem = static_cast<size_t>(4) * CT * XW * sizeof(float);
+  const int grid = hl * nchunks;
+  auto cu = reinterpret_cast<unsigned long long*>(counts);
+  const float sh = lr_scale(hl, H), sw = lr_scale(wl, W);
+#define FUVS_LR(CNT_, LG_)                                                                                              \
+  do {                                                                                                                  \
+    auto kern = linear_lowres_kernel<CT, CNT_, LG_>;                                                                    \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) \
+      return set_error(FUVS_ECUDA, "linear_lowres: cannot reserve %zu bytes of shared memory", smem);                   \
+    kern<<<grid, LR_THREADS, smem, st>>>(prev_lr, next_lr, hl, wl, H, W, n, sh, sw, XW, nchunks, labels, logits,        \
+                                         tc_prev, cu, ignore_index, w, 1.0f);                                           \
+  } while (0)
+  if (counts) { if (logits) FUVS_LR(true, true); else FUVS_LR(true, false); }
+  else        { if (logits) FUVS_LR(false, true); else FUVS_LR(false, false); }
+#undef FUVS_LR
+  return check_launch("fuvs_linear_lowres_blend_argmax");
+}
+
 // Generic class count (C <= 256 when labels/counts are requested): class loop
 // inside the frame loop, key-frame values re-read through L1.
 template <int VEC>
@@ -628,4 +761,39 @@ extern "C" int fuvs_linear_blend_argmax(const float* prev, const float* next, in
                     (!labels || aligned4(labels)) && (!tc_prev || aligned4(tc_prev));
   if (vec4) return launch_by_c<4>(C, prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
   return launch_by_c<1>(C, prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+}
+
+extern "C" int fuvs_linear_lowres_supported(int C, int H, int W) {
+  return (C >= 2 && C <= 5 && (W % 4) == 0) ? 1 : 0;
+}
+
+extern "C" int fuvs_linear_lowres_blend_argmax(const float* prev_lr, const float* next_lr, int C, int hl, int wl, int H,
+                                               int W, int n, uint8_t* labels, float* logits, const uint8_t* tc_prev,
+                                               long long* counts, int ignore_index, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  if (!prev_lr || C < 1 || hl < 1 || wl < 1 || H < 1 || W < 1 || n < 1)
+    return set_error(FUVS_EINVAL, "linear_lowres: bad shape C=%d %dx%d -> %dx%d n=%d", C, hl, wl, H, W, n);
+  if (hl == H && wl == W)     // the reference skips the interpolate when the sizes match (flow/model.py:191)
+    return fuvs_linear_blend_argmax(prev_lr, next_lr, C, H, W, n, labels, logits, tc_prev, counts, ignore_index, stream);
+  if (n > 1 && !next_lr) return set_error(FUVS_EINVAL, "linear_lowres: next key frame is NULL but n=%d", n);
+  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "linear_lowres: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
+  if (!fuvs_linear_lowres_supported(C, H, W))
+    return set_error(FUVS_EINVAL, "linear_lowres: needs 2 <= C <= 5 and W %% 4 == 0 (C=%d W=%d); up-sample with "
+                     "fuvs_upsample_bilinear_ac and call fuvs_linear_blend_argmax instead", C, W);
+  if (counts && ignore_index >= 0 && ignore_index < C)
+    return set_error(FUVS_EINVAL, "linear_lowres: ignore_index=%d collides with a class", ignore_index);
+  if (static_cast<long long>(hl) * wl * C >= (1ll << 31)) return set_error(FUVS_EINVAL, "linear_lowres: source too large");
+  if ((logits && !aligned16(logits)) || (labels && !aligned4(labels)) || (tc_prev && !aligned4(tc_prev)))
+    return set_error(FUVS_EALIGN, "linear_lowres: logits must be 16-byte, label maps 4-byte aligned");
+  if (!labels && !logits && !counts) return FUVS_OK;
+  BlendWeights w;
+  make_blend_weights(n, &w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (C) {
+    case 2: return launch_lowres<2>(prev_lr, next_lr, hl, wl, H, W, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    case 3: return launch_lowres<3>(prev_lr, next_lr, hl, wl, H, W, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    case 4: return launch_lowres<4>(prev_lr, next_lr, hl, wl, H, W, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    default: return launch_lowres<5>(prev_lr, next_lr, hl, wl, H, W, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  }
 }

@@ -167,17 +167,21 @@ class FlowModel(nn.Module):
             return self.predict_feature(*args, **kwargs)
         return self.predict_segmentation(*args, **kwargs)
 
-    def _keyframe_logits(self, frame, h, w, profiler):
+    def _keyframe_logits(self, frame, h, w, profiler, keep_lowres=False):
+        """decoder(encoder(frame)) brought to (h,w) (flow/model.py:188-193).  keep_lowres: hand back the decoder
+        output itself — the linear route evaluates the up-sample inside the blend kernel."""
         with profiler.profile("predict_encoder"):
             f = self.model.encoder(frame)
         with profiler.profile("predict_decoder"):
-            o = _interp_ac(self.model.decoder(f), h, w)
+            o = self.model.decoder(f)
+            if not (keep_lowres and not _grad_needed(o) and o.is_cuda):
+                o = _interp_ac(o, h, w)
         return o
 
     def _cached_keyframe(self, frame_id, shape):
         c = self._kf_cache
         if self.reuse_keyframes and frame_id is not None and c is not None and c[0] == frame_id and \
-                tuple(c[1].shape[-2:]) == tuple(shape):
+                tuple(c[2]) == tuple(shape):
             return c[1]
         return None
 
@@ -191,20 +195,27 @@ class FlowModel(nn.Module):
         return "dense" if (hg == h and wg == w) else "block"
 
     def _run_interval(self, o, o_next, mvs_left, mvs_right, n, *, want_labels, want_logits, tc_prev=None, counts=None,
-                      ignore_index=255, profiler=None):
+                      ignore_index=255, profiler=None, size=None):
         """Key-frame logits [1,C,h,w] x2 -> (labels [n,h,w] uint8, logits [n,C,h,w]) through one fused call."""
         kernels.require_cuda(o, o_next, what="FlowModel.predict")
         if o.shape[0] != 1:
             raise FuvsError("FlowModel.predict: the inference path takes one clip interval at a time (batch size 1, "
                             "as asserted by flow/base.py:263)")
-        h, w = o.shape[2], o.shape[3]
+        if size is None:
+            size = (o.shape[2], o.shape[3])
+        h, w = size
         if o_next is None:
             n = 1
         mode = self._interval_mode(mvs_left, h, w) if n > 1 else "linear"
         kw = dict(want_labels=want_labels, want_logits=want_logits, tc_prev=tc_prev, counts=counts,
                   ignore_index=ignore_index)
         if mode == "linear":
+            if (o.shape[2], o.shape[3]) != (h, w):            # key frames still at decoder resolution
+                return kernels.linear_lowres_blend_argmax(o, o_next, (h, w), n, **kw)
             return kernels.linear_blend_argmax(o, o_next, n, **kw)
+        if (o.shape[2], o.shape[3]) != (h, w):                # warp modes consume full-resolution key frames
+            o = _interp_ac(o, h, w)
+            o_next = _interp_ac(o_next, h, w) if o_next is not None else None
         if len(mvs_left) != n - 1 or len(mvs_right) != n - 1:
             raise FuvsError(f"FlowModel.predict: n={n} needs {n - 1} grids per side, got {len(mvs_left)}/{len(mvs_right)}")
         if mode == "dense":
@@ -214,15 +225,17 @@ class FlowModel(nn.Module):
     def predict_segmentation(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler):
         """flow/model.py:184-241 -> {"pred": [n,C,h,w]} (frame 0 = key-frame logits)."""
         h, w = frame_prev.shape[2], frame_prev.shape[3]
-        o = self._keyframe_logits(frame_prev, h, w, profiler)
+        lowres = bool(self.no_warp) and frame_next is not None
+        o = self._keyframe_logits(frame_prev, h, w, profiler, keep_lowres=lowres)
         if frame_next is None:
             return {"pred": o}
-        o_next = self._keyframe_logits(frame_next, h, w, profiler)
+        o_next = self._keyframe_logits(frame_next, h, w, profiler, keep_lowres=lowres)
         if _grad_needed(o, o_next):
             return {"pred": self._predict_segmentation_autograd(o, o_next, mvs_left, mvs_right, n, h, w)}
         with profiler.profile("predict_warp"):
             with profiler.profile("predict_fusion"):
-                _, logits = self._run_interval(o, o_next, mvs_left, mvs_right, n, want_labels=False, want_logits=True)
+                _, logits = self._run_interval(o, o_next, mvs_left, mvs_right, n, want_labels=False, want_logits=True,
+                                               size=(h, w))
         return {"pred": logits}
 
     def predict_labels(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler, *, tc_prev=None, counts=None,
@@ -237,17 +250,18 @@ class FlowModel(nn.Module):
             return labels
         h, w = frame_prev.shape[2], frame_prev.shape[3]
         with torch.no_grad():
+            lowres = bool(self.no_warp) and frame_next is not None
             o = self._cached_keyframe(frame_id, (h, w))
             if o is None:
-                o = self._keyframe_logits(frame_prev, h, w, profiler)
-            o_next = self._keyframe_logits(frame_next, h, w, profiler) if frame_next is not None else None
+                o = self._keyframe_logits(frame_prev, h, w, profiler, keep_lowres=lowres)
+            o_next = self._keyframe_logits(frame_next, h, w, profiler, keep_lowres=lowres) if frame_next is not None else None
             if self.reuse_keyframes and frame_id is not None and o_next is not None:
-                self._kf_cache = (int(frame_id) + int(n), o_next)
+                self._kf_cache = (int(frame_id) + int(n), o_next, (h, w))
             with profiler.profile("predict_warp"):
                 with profiler.profile("predict_fusion"):
                     labels, _ = self._run_interval(o, o_next, mvs_left, mvs_right, n, want_labels=True,
                                                    want_logits=False, tc_prev=tc_prev, counts=counts,
-                                                   ignore_index=ignore_index)
+                                                   ignore_index=ignore_index, size=(h, w))
         return labels
 
     def predict_feature(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler):

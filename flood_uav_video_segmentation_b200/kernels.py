@@ -55,6 +55,35 @@ def linear_blend_argmax(prev, nxt, n, *, want_labels=True, want_logits=False, tc
     return labels, logits
 
 
+def linear_lowres_blend_argmax(prev_lr, nxt_lr, size, n, *, want_labels=True, want_logits=False, tc_prev=None,
+                               counts=None, ignore_index=255):
+    """fuvs_linear_lowres_blend_argmax: key frames at decoder resolution [C,hl,wl] / [1,C,hl,wl], output size (H,W).
+
+    Shapes the fused kernel does not take (C > 5, W % 4 != 0) go through fuvs_upsample_bilinear_ac +
+    fuvs_linear_blend_argmax — the same arithmetic in two launches."""
+    dev = require_cuda(prev_lr, nxt_lr, tc_prev, counts, what="linear_lowres_blend_argmax")
+    prev_lr = _f32c(prev_lr, "prev_lr")
+    C, hl, wl = prev_lr.shape[-3:]
+    H, W = int(size[0]), int(size[1])
+    if n > 1:
+        nxt_lr = _f32c(nxt_lr, "next_lr")
+        if nxt_lr.shape[-3:] != prev_lr.shape[-3:]:
+            raise FuvsError("linear_lowres_blend_argmax: key frames differ in shape")
+    if not load().fuvs_linear_lowres_supported(C, H, W) or (counts is not None and 0 <= ignore_index < C):
+        up = upsample_bilinear_ac(prev_lr.reshape(1, C, hl, wl), (H, W))
+        up_n = upsample_bilinear_ac(nxt_lr.reshape(1, C, hl, wl), (H, W)) if n > 1 else None
+        return linear_blend_argmax(up, up_n, n, want_labels=want_labels, want_logits=want_logits, tc_prev=tc_prev,
+                                   counts=counts, ignore_index=ignore_index)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if want_labels else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_linear_lowres_blend_argmax(ptr(prev_lr), ptr(nxt_lr) if n > 1 else None, C, hl, wl, H, W, n,
+                                                     ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts), ignore_index,
+                                                     stream_ptr(dev)))
+    return labels, logits
+
+
 def _check_tc(tc_prev, counts, H, W, K):
     if tc_prev is not None:
         if tc_prev.dtype != torch.uint8 or tuple(tc_prev.shape[-2:]) != (H, W) or not tc_prev.is_contiguous():

@@ -95,6 +95,27 @@ FUVS_API int fuvs_linear_blend_argmax(const float* prev, const float* next,
                              int ignore_index, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Linear temporal blending with the key frames given at DECODER resolution
+ * (SURVEY.md §8f rank 1).  Replaces, in addition to what
+ * fuvs_linear_blend_argmax replaces, the two F.interpolate(bilinear,
+ * align_corners=True) calls that bring the decoder output to the frame size
+ * (flow/model.py:191-193, 205-206): frame p = fl(fl(w0p*up(prev_lr)) +
+ * fl(w1p*up(next_lr))), the up-sample evaluated on the fly with ATen's
+ * arithmetic, so the 2*C*H*W*4 bytes of full-resolution logits are never
+ * written.  prev_lr,next_lr : [C,hl,wl]; everything else as in
+ * fuvs_linear_blend_argmax (labels [n,H,W], logits [n,C,H,W], ...).
+ * hl==H && wl==W forwards to fuvs_linear_blend_argmax.  Supported when
+ * fuvs_linear_lowres_supported(C,H,W) != 0 (2 <= C <= 5, W % 4 == 0);
+ * otherwise FUVS_EINVAL: up-sample with fuvs_upsample_bilinear_ac first.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_linear_lowres_supported(int C, int H, int W);
+FUVS_API int fuvs_linear_lowres_blend_argmax(const float* prev_lr, const float* next_lr,
+                             int C, int hl, int wl, int H, int W, int n,
+                             uint8_t* labels, float* logits,
+                             const uint8_t* tc_prev, long long* counts,
+                             int ignore_index, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * One backward-warp step: F.grid_sample(src, grid, mode="bilinear",
  * padding_mode="border", align_corners=False|True) — flow/model.py:248
  * (align_corners=0) and flow/model.py:157 (align_corners=1).

@@ -63,6 +63,33 @@ def test_linear_interval(cuda, C, H, W, n):
     assert np.array_equal(counts2.cpu().numpy(), ref_counts2)
 
 
+@pytest.mark.parametrize("C,hl,wl,H,W", [(5, 135, 240, 1080, 1920), (5, 55, 55, 433, 433), (2, 17, 25, 136, 200),
+                                         (3, 34, 60, 270, 480), (5, 40, 40, 32, 64), (4, 1, 7, 9, 52), (7, 12, 16, 96, 128),
+                                         (5, 48, 64, 48, 64)])
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_linear_lowres_interval(cuda, C, hl, wl, H, W, n):
+    """Key frames at decoder resolution: up-sample (align_corners=True) + blend + arg-max +
+    counts in one kernel vs F.interpolate followed by the reference sequence on torch-CUDA.  433x433 and C=7 take
+    the two-launch route of the wrapper, the others the fused kernel; (5,48,64,48,64) forwards to the plain entry."""
+    g = torch.Generator().manual_seed(C * 1000 + hl)
+    o_lr = (torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda)
+    o_next_lr = (torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda)
+    up = (lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)) if (hl, wl) != (H, W) else (lambda t: t)
+    dummy = [torch.zeros(1, 1, device=cuda)] * (n - 1)
+    ref_logits = fo.predict_segmentation(ident, ident, up(o_lr), up(o_next_lr) if n > 1 else None, dummy, dummy, n, no_warp=True)
+    ref_labels = fo.argmax_labels(ref_logits)
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.linear_lowres_blend_argmax(o_lr, o_next_lr if n > 1 else None, (H, W), n, want_labels=True,
+                                                        want_logits=True, tc_prev=tc_prev.to(cuda), counts=counts)
+    assert bits_equal(logits, ref_logits), f"{int((logits.view(torch.int32) != ref_logits.view(torch.int32)).sum())} logits differ"
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    labels2, none = kernels.linear_lowres_blend_argmax(o_lr, o_next_lr if n > 1 else None, (H, W), n)
+    assert none is None and torch.equal(labels2, labels)
+
+
 @pytest.mark.parametrize("C,H,W", [(5, 433, 433), (2, 270, 480), (5, 64, 96), (5, 37, 53), (6, 48, 64)])
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 6])
 def test_dense_interval(cuda, C, H, W, n):
