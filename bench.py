@@ -424,9 +424,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    # rank 0 prints exactly one line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) goes there too
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     mode = args.mode
     workload = (f"flow-warped logit interpolation (no_warp=False), {mode} flow grids, C={C}, {H}x{W}, k={K_DELTA}, "
-                f"{CLIP_FRAMES}-frame clips" if mode != "linear" else
+                f"{CLIP_FRAMES}-frame clips" if not mode.startswith("linear") else
                 f"linear logit interpolation (no_warp=True), C={C}, {H}x{W}, k={K_DELTA}, {CLIP_FRAMES}-frame clips")
     config = {"workload": workload, "classes": C, "height": H, "width": W, "frame_delta": K_DELTA, "mode": mode,
               "clips_per_step": args.clips_per_step, "intervals_per_step": args.clips_per_step * 3,

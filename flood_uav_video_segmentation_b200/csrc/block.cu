@@ -19,6 +19,9 @@
 
 namespace fuvs {
 
+int launch_block_stream_rows(const float* key0, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
+                             int n, float sh, float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev,
+                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st);
 int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
                            int ignore_index, long long* counts, cudaStream_t st);
 int launch_argmax(const float* logits, int frames, int C, long long HW, uint8_t* u8, long long* i64, cudaStream_t st);
@@ -481,6 +484,14 @@ extern "C" int fuvs_block_interval(const float* prev, const float* next, const f
         }
         if (int e = check_launch("fuvs_block_interval(stream)")) return e;
       } else {
+        // FUVS_BLOCK_STREAM=cols forces the column-strip kernel (A/B measurements); default: source-row intervals
+        static const bool want_rows = []() { const char* e = getenv("FUVS_BLOCK_STREAM"); return !(e && e[0] == 'c'); }();
+        if (want_rows) {
+          const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev,
+                                                 counts, ignore_index, w, st);
+          if (r < 0) return r;
+          if (r == 0) return FUVS_OK;
+        }
         dim3 grid((W + STHREADS - 1) / STHREADS, (H + SROWS - 1) / SROWS);
         if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
         auto cu = reinterpret_cast<unsigned long long*>(counts);

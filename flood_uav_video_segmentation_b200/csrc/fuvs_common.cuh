@@ -216,8 +216,12 @@ template <class NM>
 __device__ __forceinline__ GsTap gs_setup(float gx, float gy, int Hin, int Win, bool align_corners) {
   const float ix = gs_source_index<NM>(gx, Win, align_corners);
   const float iy = gs_source_index<NM>(gy, Hin, align_corners);
-  const float fx = floorf(ix), fy = floorf(iy);
-  const int ix_nw = static_cast<int>(fx), iy_nw = static_cast<int>(fy);
+  // floor() and the float->int conversion without the XU pipe (FRND / F2I sit on the critical path of every pixel):
+  // after clip_coordinates 0 <= ix <= size-1 < 2^22, so t = ix + 2^23 rounded DOWN is exactly 2^23 + floor(ix)
+  // (ulp(t) == 1), t - 2^23 is exact, and the low mantissa bits of t are the integer itself.
+  const float tx = __fadd_rd(ix, 8388608.f), ty = __fadd_rd(iy, 8388608.f);
+  const float fx = __fsub_rn(tx, 8388608.f), fy = __fsub_rn(ty, 8388608.f);
+  const int ix_nw = __float_as_int(tx) - 0x4B000000, iy_nw = __float_as_int(ty) - 0x4B000000;
   // ATen converts the integer corners back to float before subtracting: float(ix_nw) == fx and
   // float(ix_nw + 1) == fx + 1 exactly (integers far below 2^24), which saves four I2F conversions per pixel
   const float x_w = fx, x_e = __fadd_rn(fx, 1.f);
@@ -285,6 +289,14 @@ __device__ __forceinline__ float two_term(float wa, float a, float wb, float b) 
   if (MODE == 0) return __fmaf_rn(wa, a, __fmul_rn(wb, b));
   if (MODE == 1) return __fmaf_rn(wb, b, __fmul_rn(wa, a));
   return __fadd_rn(__fmul_rn(wa, a), __fmul_rn(wb, b));
+}
+
+// packed FP32x2 form: two IEEE-rn results per instruction, same roundings as two_term<MODE> on each half
+template <int MODE>
+__device__ __forceinline__ u64 two_term2(u64 wa2, u64 a2, u64 wb2, u64 b2, u64 one2) {
+  if (MODE == 0) return fma2_rn(wa2, a2, mul2_rn(wb2, b2));
+  if (MODE == 1) return fma2_rn(wb2, b2, mul2_rn(wa2, a2));
+  return fma2_rn(mul2_rn(wa2, a2), one2, mul2_rn(wb2, b2));     // unfused: see blend2x2 for the run-time one
 }
 
 template <class NM>

@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "fuvs_common.cuh"
+#include "pix4.cuh"
 
 namespace fuvs {
 
@@ -113,71 +114,6 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 //     adds per label), spilled to per-thread 32-bit totals before a field can
 //     overflow and REDUX-reduced once at the end of the kernel.
 // ---------------------------------------------------------------------------
-// arg-max of NPX pixels over CT classes.  NANSAFE=false is only used when no value can be NaN.
-// One arg-max step as compare + two PREDICATED MOVES.  Written in PTX because nvcc turns `take ? v : best` into
-// FSEL/SEL, which share the half-rate ALU pipe with the FSETP compares (the kernel was ALU-pipe bound: 75 of 156
-// instructions per frame, profiles/r01_ncu_linear_v3_bulk.txt); predicated moves can issue on the FMA pipe.
-__device__ __forceinline__ void argmax_step(float& best, int& idx, float v, int c) {
-  asm("{\n\t.reg .pred p;\n\t"
-      "setp.gt.f32 p, %2, %0;\n\t"
-      "@p mov.f32 %0, %2;\n\t"
-      "@p mov.s32 %1, %3;\n\t}"
-      : "+f"(best), "+r"(idx)
-      : "f"(v), "r"(c));
-}
-
-template <int CT, int NPX, bool NANSAFE>
-__device__ __forceinline__ void argmaxN(const float (&x)[CT][NPX], int (&lab)[NPX]) {
-#pragma unroll
-  for (int i = 0; i < NPX; ++i) {
-    float best = x[0][i];
-    int idx = 0;
-#pragma unroll
-    for (int c = 1; c < CT; ++c) {
-      const float v = x[c][i];
-      if (NANSAFE) {
-        const bool take = (v > best) || ((v != v) && (best == best));
-        best = take ? v : best;
-        idx = take ? c : idx;
-      } else {
-        argmax_step(best, idx, v, c);
-      }
-    }
-    lab[i] = idx;
-  }
-}
-
-// NP pixel pairs per thread: NP = 2 -> 4 pixels (128-bit loads, 32-bit label stores),
-//                            NP = 1 -> 2 pixels (64-bit loads, 16-bit label stores; half the registers, twice the warps)
-template <int NP> struct PixIO;
-template <> struct PixIO<2> {
-  static __device__ __forceinline__ void load(const float* p, u64 (&d)[2]) {
-    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
-    d[0] = pack2(t.x, t.y);
-    d[1] = pack2(t.z, t.w);
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&x)[4]) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
-  }
-  static __device__ __forceinline__ void store_labels(uint8_t* p, const int (&l)[4]) {
-    *reinterpret_cast<unsigned*>(p) = (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
-  }
-  static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
-};
-template <> struct PixIO<1> {
-  static __device__ __forceinline__ void load(const float* p, u64 (&d)[1]) {
-    const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
-    d[0] = pack2(t.x, t.y);
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&x)[2]) {
-    __stcs(reinterpret_cast<float2*>(p), make_float2(x[0], x[1]));
-  }
-  static __device__ __forceinline__ void store_labels(uint8_t* p, const int (&l)[2]) {
-    *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>((unsigned)l[0] | ((unsigned)l[1] << 8));
-  }
-  static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
-};
-
 template <int CT, int NP, bool COUNTS, bool NANSAFE, bool LOGITS = true>
 __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 (&b)[CT][NP], long long HW,
                                               long long pix, int n, uint8_t* __restrict__ labels,
@@ -523,19 +459,20 @@ linear_lowres_kernel(const float* __restrict__ prev_lr, const float* __restrict_
     // ---- phase 2: vertical two-term, blends, arg-max, counts
     for (int y = y_lo; y < y_hi; ++y) {
       const UpCoord hc = up_coord<Nm>(sh, y, hl);
+      const u64 hl0 = pack2(hc.l0, hc.l0), hl1 = pack2(hc.l1, hc.l1);
       for (int xx = tid * 4; xx < xw; xx += LR_THREADS * 4) {
         u64 a[CT][2], b[CT][2];
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
-          const float4 r0 = *reinterpret_cast<const float4*>(lr_hs + ((0 * 2 + 0) * CT + c) * XW + xx);
-          const float4 r1 = *reinterpret_cast<const float4*>(lr_hs + ((0 * 2 + 1) * CT + c) * XW + xx);
-          a[c][0] = pack2(two_term<Nm::kUpOuter>(hc.l0, r0.x, hc.l1, r1.x), two_term<Nm::kUpOuter>(hc.l0, r0.y, hc.l1, r1.y));
-          a[c][1] = pack2(two_term<Nm::kUpOuter>(hc.l0, r0.z, hc.l1, r1.z), two_term<Nm::kUpOuter>(hc.l0, r0.w, hc.l1, r1.w));
+          const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(lr_hs + ((0 * 2 + 0) * CT + c) * XW + xx);
+          const ulonglong2 r1 = *reinterpret_cast<const ulonglong2*>(lr_hs + ((0 * 2 + 1) * CT + c) * XW + xx);
+          a[c][0] = two_term2<Nm::kUpOuter>(hl0, r0.x, hl1, r1.x, one2);
+          a[c][1] = two_term2<Nm::kUpOuter>(hl0, r0.y, hl1, r1.y, one2);
           if (n > 1) {
-            const float4 s0 = *reinterpret_cast<const float4*>(lr_hs + ((1 * 2 + 0) * CT + c) * XW + xx);
-            const float4 s1 = *reinterpret_cast<const float4*>(lr_hs + ((1 * 2 + 1) * CT + c) * XW + xx);
-            b[c][0] = pack2(two_term<Nm::kUpOuter>(hc.l0, s0.x, hc.l1, s1.x), two_term<Nm::kUpOuter>(hc.l0, s0.y, hc.l1, s1.y));
-            b[c][1] = pack2(two_term<Nm::kUpOuter>(hc.l0, s0.z, hc.l1, s1.z), two_term<Nm::kUpOuter>(hc.l0, s0.w, hc.l1, s1.w));
+            const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(lr_hs + ((1 * 2 + 0) * CT + c) * XW + xx);
+            const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(lr_hs + ((1 * 2 + 1) * CT + c) * XW + xx);
+            b[c][0] = two_term2<Nm::kUpOuter>(hl0, s0.x, hl1, s1.x, one2);
+            b[c][1] = two_term2<Nm::kUpOuter>(hl0, s0.y, hl1, s1.y, one2);
           } else {
             b[c][0] = zero2;
             b[c][1] = zero2;
