@@ -41,6 +41,8 @@ SIGNATURES = {
     "fuvs_dense_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_block_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_feature_scratch_floats": (_ll, [_i, _i, _i, _i, _i, _i]),
+    "fuvs_feature_interval": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fuvs_upsample_bilinear_ac": (_i, [_p, _p, _ll, _i, _i, _i, _i, _p]),
     "fuvs_blend_argmax": (_i, [_p, _p, _d, _d, _i, _i, _ll, _p, _p, _p]),
     "fuvs_argmax": (_i, [_p, _i, _i, _ll, _p, _p, _p]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfuvs.so")
-SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "dense_strip.cu", "block.cu", "block_rows.cu", "pointwise.cu", "crop.cu", "metric.cu", "calib.cu"]
+SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "dense_strip.cu", "block.cu", "block_rows.cu", "pointwise.cu", "feature.cu", "crop.cu", "metric.cu", "calib.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

@@ -1,0 +1,131 @@
+// feature.cu — feature-level interpolation of one interval (model.feature_based=True), SURVEY.md §8f rank 2.
+//
+// fuvs_feature_interval <- FlowModel.predict_feature, flow/model.py:131-173: the two warp chains over encoder
+// features, the per-step up-sample back to the feature size (align_corners=True, :138-139, :149-150), the temporal
+// blend (:166-171), the key frame's own pass through the default grid with align_corners=True (:154-159, sic) and
+// the torch.cat into the decoder batch (:173).  The reference materialises every up-sampled state
+// (2(n-1) x [C,fh,fw], 265 MB each for DeepLabv3 features at 1080p) and then reads them back for the blend; here the
+// chain states stay at grid resolution and one kernel writes each blended frame straight into its slot of the decoder
+// batch: up-sample of both states + blend per output element, 4 consecutive pixels per thread.
+#include "fuvs_common.cuh"
+
+namespace fuvs {
+
+int launch_warp_step_nm(const float* src0, const float* grid0, float* dst0, const float* src1, const float* grid1,
+                        float* dst1, int C, int Hin, int Win, int Hg, int Wg, int align_corners, cudaStream_t st);
+
+namespace {
+
+// out[p][c][y][x..x+VEC) = fl(fl(w0p * up(L_p)) + fl(w1p * up(R_{n-p}))) for p = 1..n-1
+template <int VEC>
+__global__ void __launch_bounds__(256)
+feature_up_blend_kernel(const float* __restrict__ Lst, const float* __restrict__ Rst, float* __restrict__ out, int C,
+                        int fh, int fw, int Hg, int Wg, int n, float sh, float sw, const BlendWeights wts) {
+  const int groups = fw / VEC;
+  const long long items = static_cast<long long>(C) * fh * groups;
+  const int lplane = Hg * Wg;
+  const long long ls = static_cast<long long>(C) * lplane;
+  const long long oplane = static_cast<long long>(fh) * fw;
+  for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < items;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(t % groups);
+    const long long r = t / groups;
+    const int y = static_cast<int>(r % fh), c = static_cast<int>(r / fh);
+    const UpCoord hc = up_coord<Nm>(sh, y, Hg);
+    UpCoord wc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) wc[i] = up_coord<Nm>(sw, g * VEC + i, Wg);
+    for (int p = 1; p < n; ++p) {
+      const float* L = Lst + (p - 1) * ls + static_cast<long long>(c) * lplane;
+      const float* R = Rst + (n - p - 1) * ls + static_cast<long long>(c) * lplane;
+      FVec<VEC> o;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        o.v[i] = blend2(wts.w0[p], up_fetch<Nm>(L, Wg, hc, wc[i]), wts.w1[p], up_fetch<Nm>(R, Wg, hc, wc[i]));
+      o.store_stream(out + (static_cast<long long>(p) * C + c) * oplane + static_cast<long long>(y) * fw + g * VEC);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace fuvs
+
+extern "C" long long fuvs_feature_scratch_floats(int C, int Hg, int Wg, int Hd, int Wd, int n) {
+  long long f = 0;
+  if (n > 1) f += 2ll * (n - 1) * C * static_cast<long long>(Hg) * Wg;       // chain states of both sides
+  f += static_cast<long long>(C) * Hd * Wd;                                  // key frame warped through the default grid
+  return f;
+}
+
+extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, const float* grids_left,
+                                     const float* grids_right, const float* default_grid, int Hd, int Wd, int C, int fh,
+                                     int fw, int Hg, int Wg, int n, float* scratch, float* out, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (int e = device_ok()) return e;
+  if (!f_prev || !out || C < 1 || fh < 1 || fw < 1 || n < 1)
+    return set_error(FUVS_EINVAL, "feature_interval: bad shape C=%d %dx%d n=%d", C, fh, fw, n);
+  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "feature_interval: n=%d exceeds %d frames", n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!f_next || !grids_left || !grids_right || Hg < 1 || Wg < 1))
+    return set_error(FUVS_EINVAL, "feature_interval: next/grids missing but n=%d", n);
+  if ((n > 1 || default_grid) && !scratch) return set_error(FUVS_EINVAL, "feature_interval: scratch is NULL");
+  if (default_grid && (Hd < 1 || Wd < 1)) return set_error(FUVS_EINVAL, "feature_interval: empty default grid");
+  const long long plane = static_cast<long long>(fh) * fw;
+  if (plane >= (1ll << 31) || static_cast<long long>(C) * Hg * Wg >= (1ll << 31))
+    return set_error(FUVS_EINVAL, "feature_interval: problem exceeds 32-bit indexing");
+  if ((n > 1 && (!aligned8(grids_left) || !aligned8(grids_right))) || (default_grid && !aligned8(default_grid)))
+    return set_error(FUVS_EALIGN, "feature_interval: grids must be 8-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long S = static_cast<long long>(C) * plane;
+  const long long ls = static_cast<long long>(C) * Hg * Wg;
+  float* Lst = scratch;
+  float* Rst = scratch + (n > 1 ? (n - 1) * ls : 0);
+  float* tmp0 = scratch + (n > 1 ? 2 * (n - 1) * ls : 0);
+
+  if (n > 1) {
+    // chains at grid resolution (flow/model.py:133-137, 144-148); channel-chunked launches fill the SMs for C ~ 2048
+    for (int j = 1; j <= n - 1; ++j) {
+      const float* sL = (j == 1) ? f_prev : Lst + (j - 2) * ls;
+      const float* sR = (j == 1) ? f_next : Rst + (j - 2) * ls;
+      const int Hin = (j == 1) ? fh : Hg, Win = (j == 1) ? fw : Wg;
+      if (int e = launch_warp_step_nm(sL, grids_left + static_cast<long long>(j - 1) * Hg * Wg * 2, Lst + (j - 1) * ls, sR,
+                                      grids_right + static_cast<long long>(j - 1) * Hg * Wg * 2, Rst + (j - 1) * ls, C, Hin,
+                                      Win, Hg, Wg, 0, st))
+        return e;
+    }
+    BlendWeights w;
+    make_blend_weights(n, &w);
+    if (Hg == fh && Wg == fw) {
+      // sizes match: the reference skips the interpolate (flow/model.py:138), plain blends
+      for (int p = 1; p < n; ++p) {
+        if (int e = fuvs_blend_argmax(Lst + (p - 1) * ls, Rst + (n - p - 1) * ls, static_cast<double>(n - p) / n,
+                                      static_cast<double>(p) / n, 1, C, plane, out + p * S, nullptr, stream))
+          return e;
+      }
+    } else {
+      const float sh = fh > 1 ? static_cast<float>(Hg - 1) / (fh - 1) : 0.f;
+      const float sw = fw > 1 ? static_cast<float>(Wg - 1) / (fw - 1) : 0.f;
+      const bool vec4 = (fw % 4 == 0) && aligned16(out);
+      const long long items = static_cast<long long>(C) * fh * (vec4 ? fw / 4 : fw);
+      long long grid = (items + 255) / 256;
+      const long long cap = 32ll * sm_count();
+      if (grid > cap) grid = cap;
+      if (vec4)
+        feature_up_blend_kernel<4><<<static_cast<int>(grid), 256, 0, st>>>(Lst, Rst, out, C, fh, fw, Hg, Wg, n, sh, sw, w);
+      else
+        feature_up_blend_kernel<1><<<static_cast<int>(grid), 256, 0, st>>>(Lst, Rst, out, C, fh, fw, Hg, Wg, n, sh, sw, w);
+      if (int e = check_launch("fuvs_feature_interval(up-sample + blend)")) return e;
+    }
+  }
+  // frame 0 (flow/model.py:154-159): the key frame's features through the default grid with align_corners=True,
+  // restored to the feature size; without a default grid (no_warp) the features themselves
+  if (default_grid) {
+    if (Hd == fh && Wd == fw) {
+      return launch_warp_step_nm(f_prev, default_grid, out, nullptr, nullptr, nullptr, C, fh, fw, Hd, Wd, 1, st);
+    }
+    if (int e = launch_warp_step_nm(f_prev, default_grid, tmp0, nullptr, nullptr, nullptr, C, fh, fw, Hd, Wd, 1, st)) return e;
+    return fuvs_upsample_bilinear_ac(tmp0, out, C, Hd, Wd, fh, fw, stream);
+  }
+  if (cudaMemcpyAsync(out, f_prev, S * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return set_error(FUVS_ECUDA, "feature_interval: key-frame copy failed");
+  return FUVS_OK;
+}

@@ -77,6 +77,12 @@ static int launch_warp_step(const float* src0, const float* grid0, float* dst0, 
   return check_launch("fuvs_warp_step");
 }
 
+// non-template entry for other translation units (feature.cu)
+int launch_warp_step_nm(const float* src0, const float* grid0, float* dst0, const float* src1, const float* grid1,
+                        float* dst1, int C, int Hin, int Win, int Hg, int Wg, int align_corners, cudaStream_t st) {
+  return launch_warp_step<Nm>(src0, grid0, dst0, src1, grid1, dst1, C, Hin, Win, Hg, Wg, align_corners, st);
+}
+
 // ---------------------------------------------------------------------------
 // dense lock-step kernel
 // ---------------------------------------------------------------------------

@@ -283,32 +283,21 @@ class FlowModel(nn.Module):
             f_next = f_next.contiguous().float()
         cf, f_h, f_w = f.shape[1], f.shape[2], f.shape[3]
         frames = n if f_next is not None else 1
-        feature_maps = torch.empty((frames, cf, f_h, f_w), dtype=torch.float32, device=dev)
-        fwd, bwd = [], []
-        if f_next is not None and not self.no_warp:
-            with profiler.profile("predict_warp"):
-                cur_l, cur_r = f[0], f_next[0]
-                for m_l, m_r in zip(mvs_left, mvs_right):
-                    cur_l, cur_r = kernels.warp_step(cur_l, m_l, cur_r, m_r)
-                    fwd.append(self._restore(cur_l, f_h, f_w))
-                    bwd.append(self._restore(cur_r, f_h, f_w))
         if not self.no_warp:
-            # key frame resampled through the default grid with align_corners=True (flow/model.py:154-159)
+            # one fused call: chains at grid resolution, up-sample + blend written straight into the decoder batch,
+            # key frame through the default grid with align_corners=True (flow/model.py:131-173)
             if self.default_motion_vector.device != f.device:
                 self.default_motion_vector = self.default_motion_vector.to(device=f.device)
-            f0, _ = kernels.warp_step(f[0], self.default_motion_vector, align_corners=True)
-            if f0.shape[1] != f_h or f0.shape[2] != f_w:
-                kernels.upsample_bilinear_ac(f0, (f_h, f_w), out=feature_maps[0])
-            else:
-                feature_maps[0].copy_(f0)
+            with profiler.profile("predict_warp"):
+                with profiler.profile("predict_fusion"):
+                    feature_maps = kernels.feature_interval(f[0], f_next[0] if f_next is not None else None, mvs_left,
+                                                            mvs_right, frames, default_grid=self.default_motion_vector)
         else:
+            feature_maps = torch.empty((frames, cf, f_h, f_w), dtype=torch.float32, device=dev)
             feature_maps[0].copy_(f[0])
-        if f_next is not None:
-            with profiler.profile("predict_fusion"):
-                for p in range(1, n):
-                    if not self.no_warp:
-                        kernels.blend_argmax(fwd[p - 1], bwd[n - p - 1], (n - p) / n, p / n, out=feature_maps[p])
-                    else:
+            if f_next is not None:
+                with profiler.profile("predict_fusion"):
+                    for p in range(1, n):
                         # the reference blends the *resampled* key frame only when warping; here f is untouched
                         kernels.blend_argmax(f[0], f_next[0], (n - p) / n, p / n, out=feature_maps[p])
         with profiler.profile("predict_decoder"):

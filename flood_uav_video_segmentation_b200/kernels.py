@@ -306,3 +306,34 @@ def crop_finish(canvas, count, *, want_labels=True):
     with torch.cuda.device(dev):
         check(load().fuvs_crop_finish(ptr(canvas), ptr(count), n, Cc, H * W, ptr(labels), stream_ptr(dev)))
     return labels
+
+
+def feature_interval(f_prev, f_next, grids_left, grids_right, n, *, default_grid=None, scratch=None, out=None):
+    """fuvs_feature_interval: predict_feature's warp / up-sample / blend / cat (flow/model.py:131-173) -> [n,C,fh,fw]."""
+    dev = require_cuda(f_prev, f_next, default_grid, out, what="feature_interval")
+    f_prev = _f32c(f_prev, "f_prev")
+    C, fh, fw = f_prev.shape[-3:]
+    gl = gr = None
+    Hg = Wg = 0
+    if n > 1:
+        f_next = _f32c(f_next, "f_next")
+        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
+        require_cuda(gl, gr, what="feature_interval(grids)")
+        Hg, Wg = gl.shape[1:3]
+        if tuple(gl.shape) != (n - 1, Hg, Wg, 2) or tuple(gr.shape) != tuple(gl.shape):
+            raise FuvsError("feature_interval: grids must both be [n-1,Hg,Wg,2]")
+    Hd = Wd = 0
+    if default_grid is not None:
+        default_grid = _f32c(default_grid if default_grid.dtype == torch.float32 else default_grid.float(), "default_grid")
+        Hd, Wd = default_grid.shape[-3:-1]
+    need = int(load().fuvs_feature_scratch_floats(C, Hg, Wg, Hd, Wd, n))
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n, C, fh, fw), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (n, C, fh, fw) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise FuvsError("feature_interval: bad `out` tensor")
+    with torch.cuda.device(dev):
+        check(load().fuvs_feature_interval(ptr(f_prev), ptr(f_next) if n > 1 else None, ptr(gl), ptr(gr), ptr(default_grid),
+                                           Hd, Wd, C, fh, fw, Hg, Wg, n, ptr(scratch), ptr(out), stream_ptr(dev)))
+    return out

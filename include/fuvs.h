@@ -172,6 +172,27 @@ FUVS_API int fuvs_block_interval(const float* prev, const float* next,
                         int ignore_index, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Feature-level interval (model.feature_based=True) — FlowModel.predict_feature,
+ * flow/model.py:131-173: both warp chains over the encoder features, the
+ * up-sample of every chain state back to the feature size (align_corners=
+ * True), the temporal blend and the concatenation into the decoder batch.
+ *   f_prev,f_next : [C,fh,fw] encoder features of the two key frames
+ *   grids_*       : [n-1,Hg,Wg,2]
+ *   default_grid  : [Hd,Wd,2] FlowModel.default_motion_vector or NULL; when
+ *                   given, frame 0 = up(grid_sample(f_prev, default_grid,
+ *                   align_corners=True)) exactly as flow/model.py:154-159,
+ *                   else frame 0 = f_prev
+ *   scratch       : fuvs_feature_scratch_floats(C,Hg,Wg,Hd,Wd,n) floats
+ *   out           : [n,C,fh,fw] — the tensor the decoder is called on
+ * ------------------------------------------------------------------------- */
+FUVS_API long long fuvs_feature_scratch_floats(int C, int Hg, int Wg, int Hd, int Wd, int n);
+FUVS_API int fuvs_feature_interval(const float* f_prev, const float* f_next,
+                          const float* grids_left, const float* grids_right,
+                          const float* default_grid, int Hd, int Wd,
+                          int C, int fh, int fw, int Hg, int Wg, int n,
+                          float* scratch, float* out, fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * F.interpolate(src, size=(Hout,Wout), mode="bilinear", align_corners=True)
  * — flow/model.py:42,68,86,103,139,150,159,179,193,206,218,228 and
  * flow/base.py:219,232,275.   src [N*C,Hin,Win] -> dst [N*C,Hout,Wout].

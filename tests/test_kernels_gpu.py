@@ -155,6 +155,32 @@ def test_dense_interval_tma_path_and_large_motion(cuda, jitter, C, H, W, n):
     assert torch.equal(labels2, labels)
 
 
+@pytest.mark.parametrize("C,fh,fw,hg,wg", [(48, 40, 64, 20, 32), (48, 40, 64, 40, 64), (7, 33, 50, 16, 25), (130, 17, 24, 8, 12)])
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_feature_interval(cuda, C, fh, fw, hg, wg, n):
+    """fuvs_feature_interval vs the restated FlowModel.predict_feature (flow/model.py:116-181) with identity encoder /
+    decoder on torch-CUDA: chains at grid resolution, up-sample + blend into the decoder batch, key frame through the
+    default grid with align_corners=True."""
+    g = torch.Generator().manual_seed(C + fh)
+    f, f_next = torch.randn(1, C, fh, fw, generator=g).to(cuda), torch.randn(1, C, fh, fw, generator=g).to(cuda)
+    base = torch.stack(torch.meshgrid((torch.arange(hg) + 0.5) / hg * 2 - 1, (torch.arange(wg) + 0.5) / wg * 2 - 1,
+                                      indexing="ij")[::-1], -1)
+
+    def grids():
+        return [(base + (torch.rand(base.shape, generator=g) - 0.5) * 0.2).unsqueeze(0).to(cuda) for _ in range(n - 1)]
+
+    gl, gr = grids(), grids()
+    default = torch.stack(torch.meshgrid((torch.arange(9) + 0.5) / 9 * 2 - 1, (torch.arange(13) + 0.5) / 13 * 2 - 1,
+                                         indexing="ij")[::-1], -1).unsqueeze(0).float().to(cuda)
+    ref = fo.predict_feature(ident, ident, f, f_next if n > 1 else None, gl, gr, n, default)
+    got = kernels.feature_interval(f, f_next if n > 1 else None, gl, gr, n, default_grid=default)
+    assert got.shape == ref.shape
+    assert bits_equal(got, ref), f"{int((got.view(torch.int32) != ref.view(torch.int32)).sum())} elements differ"
+    # without a default grid frame 0 is the key frame's features themselves
+    got2 = kernels.feature_interval(f, f_next if n > 1 else None, gl, gr, n)
+    assert bits_equal(got2[0], f[0]) and bits_equal(got2[1:], ref[1:])
+
+
 def test_full_size_1080p_all_modes(cuda):
     """BASELINE.json configs at full size, one interval each, against the oracle on torch-CUDA."""
     C, H, W, n = 5, 1080, 1920, 5
