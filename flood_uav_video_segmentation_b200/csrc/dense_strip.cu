@@ -34,6 +34,9 @@ using namespace tma;
 
 constexpr int TW = 128;                      // strip width = threads per thread-row
 constexpr int HALO_X = 32, HALO_Y = 16;
+// Row stride 192 = 0 mod 32 banks on purpose: with coherent flow a warp's taps straddle at most two rows and stay
+// conflict-free whatever the rows are.  A skewed stride (196) was measured: it spreads the taps that border clipping
+// sends to one column (edge strips, iid flow: -1 %) but costs coherent flow 5 % (2-way conflicts at row changes).
 constexpr int BOXW = TW + 2 * HALO_X;        // 192
 constexpr int RB = 8;                        // rows per block = rows per ring slot
 constexpr int WIN = (RB + 2 * HALO_Y) / RB;  // 5 slots cover the window of one block
@@ -56,6 +59,7 @@ __device__ int g_strip_dbg;   // bit 0: no tap loads, 1: no state stores, 2: fix
 struct StripGeom {
   int nsx, nby, total, nslot;
   int wl, wr;                                // relative cost of a forward-side / backward-side block (CTA partition)
+  int wedge;                                 // cost of a block of the two edge strips, in eighths
 };
 struct StripMaps {
   CUtensorMap srcL, srcR;                    // [C][H][W] fp32, box BOXW x RB x C
@@ -140,14 +144,25 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
   const int lane = tid & 31;
   const int tx = tid & (TW - 1), ty = tid >> 7;                        // TW == 128
   const int HWi = H * W;                                               // the host guarantees C*H*W < 2^31
-  // CTA b takes the blocks whose cumulative cost lies in [b, b+1) * total_cost / grid: the forward side comes first
-  // in the numbering, so a cost position maps back to a block index piecewise linearly
-  const int half = G.total >> 1;
-  const long long cost_l = static_cast<long long>(half) * G.wl, cost_all = cost_l + static_cast<long long>(half) * G.wr;
+  // CTA b takes the blocks whose cumulative cost lies in [b, b+1) * total_cost / grid.  A block's cost is
+  // side weight (step 1: the forward side also emits frame 0) x strip weight (the two strips at the image edge cost
+  // ~12 % more: border clipping sends many lanes to the same column, i.e. the same shared-memory bank).
+  auto unit_w = [&](int u) {
+    const bool side = u >= G.nsx;
+    const int strip = side ? u - G.nsx : u;
+    const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
+    return (side ? G.wr : G.wl) * (edge ? G.wedge : 8);
+  };
+  long long cost_all = 0;
+  for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u);
   auto block_at = [&](long long num) {        // first block whose start cost is >= num * cost_all / grid
-    const long long pos = (num * cost_all + gridDim.x - 1) / gridDim.x;
-    if (pos <= cost_l) return static_cast<int>((pos + G.wl - 1) / G.wl);
-    return half + static_cast<int>((pos - cost_l + G.wr - 1) / G.wr);
+    long long pos = (num * cost_all + gridDim.x - 1) / gridDim.x;
+    for (int u = 0; u < 2 * G.nsx; ++u) {
+      const long long w = unit_w(u), cu = static_cast<long long>(G.nby) * w;
+      if (pos <= cu) return u * G.nby + static_cast<int>((pos + w - 1) / w);
+      pos -= cu;
+    }
+    return G.total;
   };
   const int B0 = block_at(blockIdx.x);
   const int B1 = (blockIdx.x + 1 == gridDim.x) ? G.total : block_at(blockIdx.x + 1);
@@ -433,6 +448,8 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.nslot = nslot;
   g.wl = KEY0 ? 5 : 4;                         // measured: frame 0 costs the forward side ~25 % more per block
   g.wr = 4;
+  static const int wedge = []() { const char* e = getenv("FUVS_STRIP_WEDGE"); return e ? atoi(e) : 9; }();
+  g.wedge = wedge;
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
   static const bool pdl = []() { const char* e = getenv("FUVS_STRIP_PDL"); return !(e && e[0] == '0'); }();
