@@ -431,16 +431,10 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 
 template <int CT, int NSC, int TROWS, bool EMIT, bool KEY0>
 int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
-  static bool attr_done = false;
+  static SmemOptIn optin;
   auto kern = dense_strip_kernel<Nm, CT, NSC, TROWS, EMIT, KEY0>;
   const size_t smem = static_cast<size_t>(nslot) * C * PLANE * 4 + 256;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
-      cudaGetLastError();
-      return 1;
-    }
-    attr_done = true;
-  }
+  if (!optin.ensure(kern, SMEM_LIMIT)) return 1;
   StripGeom g;
   g.nsx = (W + TW - 1) / TW;
   g.nby = (H + RB - 1) / RB;

@@ -8,12 +8,12 @@
 // channel plane (cp.async.bulk.tensor.3d -> UTMALDG, completion on an mbarrier),
 // three planes in flight, and the taps become shared-memory loads.
 //
-// Work item = (128x32 output tile, side).  The forward and the backward chain of
-// a step are independent, so 2 * tiles items are spread round-robin over a
-// persistent grid of one 512-thread CTA per SM (1020 items on 148 SMs at 1080p).
-// The window is a fixed 192x64 box centred on the tile (halo 32 px in x, 16 px in
-// y); an item whose taps leave the box (large motion) gathers from global memory
-// instead (block-uniform decision), so any flow field stays correct.
+// Work item = (128x16 output tile, side).  The forward and the backward chain of a step are independent, so
+// 2 * tiles items are spread round-robin over a persistent grid of two 512-thread CTAs per SM (2040 items at 1080p).
+// The window is a fixed 192x48 box around the tile (halo 32 px in x, 16 px in y), one channel plane at a time through
+// three buffers; a warp whose taps leave the box (large motion) gathers from global memory instead, so any flow
+// field stays correct.  Since dense_strip.cu (all channels resident, 1.5x instead of 4.5x fabric amplification) this
+// kernel is the fall-back for class counts whose window does not fit shared memory (C > 6).
 // Arithmetic is gs_setup/tap_acc from fuvs_common.cuh: bit-identical to the
 // direct kernel and to ATen's grid_sampler_2d.
 #include <cuda.h>
@@ -29,9 +29,9 @@ constexpr int TROWS = 4;                    // thread rows per CTA
 constexpr int PX = TH / TROWS;              // pixels per thread (one column, stride TROWS rows)
 constexpr int HALO_X = 32, HALO_Y = 16;
 constexpr int BOXW = TW + 2 * HALO_X;       // 192
-constexpr int BOXH = TH + 2 * HALO_Y;       // 64
+constexpr int BOXH = TH + 2 * HALO_Y;       // 48
 constexpr int NBUF = 3;
-constexpr int BOX_BYTES = BOXW * BOXH * 4;  // 49152
+constexpr int BOX_BYTES = BOXW * BOXH * 4;  // 36864
 constexpr int THREADS = TW * TROWS;         // 512
 constexpr size_t SMEM_BYTES = static_cast<size_t>(NBUF) * BOX_BYTES + 128;   // + 2*NBUF mbarriers
 
@@ -451,15 +451,9 @@ bool make_grid_map(CUtensorMap* m, const float* ptr, int H, int W) {
 
 template <int CT, bool EMIT, bool KEY0>
 int launch_variant(const TmaMaps& maps, const DenseStep& a, int C, int H, int W, cudaStream_t st) {
-  static bool attr_done = false;
+  static SmemOptIn optin;
   auto kern = dense_step_tma_kernel<Nm, CT, EMIT, KEY0>;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(SMEM_BYTES)) != cudaSuccess) {
-      cudaGetLastError();
-      return 1;
-    }
-    attr_done = true;
-  }
+  if (!optin.ensure(kern, static_cast<int>(SMEM_BYTES))) return 1;
   TileGeom g;
   g.tiles_x = (W + TW - 1) / TW;
   g.tiles_y = (H + TH - 1) / TH;

@@ -38,6 +38,23 @@ int blocks_per_sm(K kernel, int threads, size_t smem = 0) {
   return nb;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per device whether a kernel has it.
+struct SmemOptIn {
+  bool done[64] = {};
+  template <typename K>
+  bool ensure(K kernel, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (done[dev]) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    done[dev] = true;
+    return true;
+  }
+};
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }

@@ -379,14 +379,8 @@ static int launch_bulk(const float* prev, const float* next, long long HW, int n
                        cudaStream_t st) {
   const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + 64;
   auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) {
-      cudaGetLastError();
-      return 1;                                  // caller uses the register-load kernel
-    }
-    attr_done = true;
-  }
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, static_cast<int>(smem))) return 1;   // caller uses the register-load kernel
   const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
   const long long cap = sm_count();
   const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
