@@ -336,3 +336,48 @@ def test_errors_are_loud(cuda):
         kernels.linear_blend_argmax(torch.zeros(5, 8, 8, device=cuda), torch.zeros(5, 8, 8, device=cuda), 500)
     with pytest.raises(kernels.FuvsError):
         kernels.confusion(torch.zeros(4, device=cuda), torch.zeros(4, dtype=torch.int64, device=cuda), 5)
+
+
+def test_limits_and_degenerate_shapes(cuda):
+    """Maximum interval length (60 frames), maximum class count for uint8 label maps (256), one-pixel frames, empty
+    metric inputs, and the loud failures just beyond the limits."""
+    g = torch.Generator().manual_seed(11)
+    # n = FUVS_MAX_FRAMES through the linear entry (C = 3: field counters spill many times)
+    C, H, W, n = 3, 24, 32, 60
+    o, o_next = torch.randn(1, C, H, W, generator=g), torch.randn(1, C, H, W, generator=g)
+    dummy = [torch.zeros(1, 1)] * (n - 1)
+    ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o, o_next, dummy, dummy, n, no_warp=True))
+    counts = kernels.new_counts(C, cuda)
+    labels, _ = kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), n, counts=counts)
+    assert torch.equal(labels.cpu().long(), ref)
+    ref_counts, _ = oracle_temporal(ref, C, None)
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    with pytest.raises(kernels.FuvsError):
+        kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), 61)
+    # C = 256 classes: generic-C kernels, uint8 labels up to 255, shared-memory histogram counts
+    C, H, W, n = 256, 9, 12, 3
+    o, o_next = torch.randn(1, C, H, W, generator=g), torch.randn(1, C, H, W, generator=g)
+    dummy = [torch.zeros(1, 1)] * (n - 1)
+    ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o, o_next, dummy, dummy, n, no_warp=True))
+    counts = kernels.new_counts(C, cuda)
+    # ignore_index = 255 collides with class 255 here: the reference then moves ignored pixels INTO class 255
+    labels, _ = kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), n, counts=counts, ignore_index=255)
+    assert torch.equal(labels.cpu().long(), ref) and int(ref.max()) > 200
+    ref_counts, _ = oracle_temporal(ref, C, None)
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    with pytest.raises(kernels.FuvsError):
+        kernels.linear_blend_argmax(torch.zeros(1, 257, 4, 4, device=cuda), torch.zeros(1, 257, 4, 4, device=cuda), 2)
+    # one-pixel frame, every mode that accepts it
+    o, o_next = torch.tensor([[[[1.0]], [[3.0]], [[2.0]]]]), torch.tensor([[[[5.0]], [[0.0]], [[4.0]]]])
+    ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o, o_next, [torch.zeros(1, 1)] * 3, [torch.zeros(1, 1)] * 3, 4,
+                                                   no_warp=True))
+    labels, _ = kernels.linear_blend_argmax(o.to(cuda), o_next.to(cuda), 4)
+    assert torch.equal(labels.cpu().long(), ref)
+    grid = [torch.zeros(1, 1, 1, 2)] * 3
+    ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, o.to(cuda), o_next.to(cuda), [x.to(cuda) for x in grid],
+                                                   [x.to(cuda) for x in grid], 4))
+    labels, _ = kernels.dense_interval(o.to(cuda), o_next.to(cuda), [x.to(cuda) for x in grid], [x.to(cuda) for x in grid], 4)
+    assert torch.equal(labels.long(), ref)
+    # empty metric input: nothing is counted, nothing fails
+    counts = kernels.confusion(torch.zeros(0, dtype=torch.uint8, device=cuda), torch.zeros(0, dtype=torch.int64, device=cuda), 5)
+    assert int(counts.sum()) == 0
