@@ -372,7 +372,9 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
             if (w_dst && live) dst[gi] = acc;
             if (EMIT) {
               const float o = CT > 0 ? other[r][CT > 0 ? c : 0] : (live ? __ldg(point + gi) : 0.f);
-              const float v = side ? blend2(w_point, o, w_this, acc) : blend2(w_this, acc, w_point, o);
+              // fl(fl(w_this*acc) + fl(w_point*o)): IEEE addition is commutative, so one operand order serves both
+              // sides (the reference adds the forward term first on both) and the code is not duplicated per side
+              const float v = blend2(w_this, acc, w_point, o);
               am[r].push(v, c);
               if (w_lp && live) __stcs(logit_out + gi, v);
             }

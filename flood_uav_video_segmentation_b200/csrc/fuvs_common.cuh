@@ -199,7 +199,8 @@ struct ArgMax {
   int idx;
   __device__ __forceinline__ void init(float v) { best = v; idx = 0; }
   __device__ __forceinline__ void push(float v, int c) {
-    const bool take = (v > best) || ((v != v) && (best == best));
+    // v > best, or v is NaN and best is not: !(v <= best) is true for both, a NaN best is never replaced
+    const bool take = !(v <= best) && (best == best);
     if (take) { best = v; idx = c; }
   }
 };
