@@ -424,9 +424,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    # rank 0 prints exactly one line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION on the GPU boxes) goes there too
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints exactly one line on stdout: keep NCCL's version banner (printed to stdout at NCCL_DEBUG >= VERSION) out
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # the GPU boxes export this; WARN would print the banner too
+        os.environ["NCCL_DEBUG"] = "NONE"
     mode = args.mode
     workload = (f"flow-warped logit interpolation (no_warp=False), {mode} flow grids, C={C}, {H}x{W}, k={K_DELTA}, "
                 f"{CLIP_FRAMES}-frame clips" if not mode.startswith("linear") else
