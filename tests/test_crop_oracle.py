@@ -85,3 +85,37 @@ def test_compute_output_oracle_matches_reference_golden():
     assert len(list(co.crop_windows(prev.shape[2], prev.shape[3], ch, cw))) == ncrops
     assert np.array_equal(canvas[:, :, ::3, ::3].numpy(), z["full_canvas_sub"])
     assert np.array_equal(canvas.max(1)[1].numpy().astype(np.uint8), z["full_labels"])
+
+
+def test_crop_properties_random_shapes():
+    """Property tests (hypothesis): the crop windows tile the frame for any frame / crop size, the host-side mirror
+    enumerates the same windows as the oracle, and the numpy restatement of cv2's bilinear resize is bit-exact for
+    arbitrary down-scales (the only direction crop_motion_vector uses)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.integers(17, 400), st.integers(17, 400), st.integers(16, 200), st.integers(16, 200))
+    def windows(new_h, new_w, crop_h, crop_w):
+        crop_h, crop_w = min(crop_h, new_h), min(crop_w, new_w)
+        w = list(co.crop_windows(new_h, new_w, crop_h, crop_w))
+        assert w == list(FlowBaseModel.crop_windows(new_h, new_w, crop_h, crop_w))
+        cover = np.zeros((new_h, new_w), bool)
+        for s_h, e_h, s_w, e_w in w:
+            assert 0 <= s_h and e_h <= new_h and 0 <= s_w and e_w <= new_w and e_h - s_h == crop_h and e_w - s_w == crop_w
+            cover[s_h:e_h, s_w:e_w] = True
+        assert cover.all()
+
+    windows()
+    cv2 = pytest.importorskip("cv2")
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(st.integers(2, 60), st.integers(2, 60), st.integers(1, 30), st.integers(1, 30), st.integers(0, 2 ** 31 - 1))
+    def resize(ih, iw, oh, ow, seed):
+        oh, ow = min(oh, ih), min(ow, iw)                      # down-scale or identity
+        m = (np.random.default_rng(seed).random((ih, iw, 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+        ref = cv2.resize(m, (ow, oh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(co.resize_linear_np(m, ow, oh).view(np.int32), ref.view(np.int32))
+
+    resize()
