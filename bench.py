@@ -372,6 +372,67 @@ def to_host_clip(clip):
     return hk, hg
 
 
+# ----------------------------------------------------------------------------- stock torch ops on the same GPU
+def stock_torch_interval(mode, keys, grids, it, last):
+    """The op sequence the reference issues for one interval, as stock ATen CUDA kernels on this GPU: grid_sample
+    chains (flow/model.py:212-229, 244-249), scalar mul / add (233-237), cat (239), max(1)[1] (flow/base.py:276) and
+    the temporal-consistency metric through intersectionAndUnionGPU with its three .cpu() reads per call
+    (flow/base.py:280-295, util/util.py:52-63, base/foundation.py:344).  Written out here, not imported from oracle/."""
+    import torch.nn.functional as F
+    n = K_DELTA
+    o, o_next = keys[it], keys[it + 1]
+    h, w = o.shape[2], o.shape[3]
+
+    def chain(x, gs):
+        outs = []
+        for g in gs:
+            x = F.grid_sample(x, g, mode="bilinear", padding_mode="border", align_corners=False)
+            outs.append(x if (x.shape[2], x.shape[3]) == (h, w) else
+                        F.interpolate(x, size=(h, w), mode="bilinear", align_corners=True))
+        return outs
+
+    if mode == "linear":
+        fwd, bwd = [o] * (n - 1), [o_next] * (n - 1)
+    else:
+        fwd = chain(o, [grids[it][0][j:j + 1] for j in range(n - 1)])
+        bwd = chain(o_next, [grids[it][1][j:j + 1] for j in range(n - 1)])
+    maps = [o]
+    for p in range(1, n):
+        maps.append((n - p) / n * fwd[p - 1] + p / n * bwd[n - p - 1])
+    labels = torch.cat(maps, 0).max(1)[1]
+
+    def metric(output, target):
+        output = output.reshape(-1).clone()
+        target = target.reshape(-1)
+        output[target == 255] = 255
+        inter = output[output == target]
+        a_i = torch.histc(inter, bins=C, min=0, max=C - 1)
+        a_o = torch.histc(output, bins=C, min=0, max=C - 1)
+        a_t = torch.histc(target, bins=C, min=0, max=C - 1)
+        return a_i.cpu().numpy(), (a_o + a_t - a_i).cpu().numpy(), a_t.cpu().numpy()
+
+    for p in range(n):
+        if p == 0 and last is None:
+            continue
+        metric(labels[p], labels[p - 1] if p > 0 else last)
+    return labels
+
+
+def time_stock_torch(mode, clip, device, intervals=6):
+    keys, grids = clip
+    n_int = len(keys) - 1
+    with torch.no_grad():
+        stock_torch_interval(mode, keys, grids, 0, None)       # warm-up
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        last, labels = None, None
+        for j in range(intervals):
+            labels = stock_torch_interval(mode, keys, grids, j % n_int, last if j % n_int else None)
+            last = labels[K_DELTA - 1]
+        torch.cuda.synchronize(device)
+    return time.perf_counter() - t0, labels
+
+
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
 def cpu_interval(mode, keys, grids, it, last):
     """The reference call sequence on torch-CPU: FlowModel.predict -> max(1)[1] -> uint8 -> numpy temporal IoU."""
@@ -499,6 +560,18 @@ def main():
                       "temporal_miou": float(res.get("predict_miou1_epoch", float("nan")))}
 
     if rank == 0 and world == 1 and not args.no_cpu:
+        # the reference's own op sequence as stock torch-CUDA kernels on the same GPU, inputs resident (context for
+        # `value`: there is no Blackwell-specific reference kernel to compare with)
+        n_st = 6
+        dt_st, lab_st = time_stock_torch(mode, clips[0], device, n_st)
+        lab_ours = run_interval(kernels, mode, clips[0][0], clips[0][1], (n_st - 1) % 3, None, None)
+        out["stock_torch_cuda"] = {"value": n_st * (K_DELTA - 1) / dt_st, "unit": "frames/s",
+                                   "us_per_interval": dt_st * 1e6 / n_st,
+                                   "sample": f"{n_st} intervals of the same {mode} workload, eager ATen kernels "
+                                             "(grid_sample, mul, add, cat, max, histc) incl. the metric's host reads",
+                                   "label_pixels_differing_from_ours": int((lab_st != lab_ours.long()).sum().item())}
+        del lab_st
+        torch.cuda.empty_cache()
         hc = host_clips[0] if host_clips else to_host_clip(clips[0])
         n_samp = 30 if mode in ("dense", "dense_smooth") else 45   # ~10-15 s of host work on the box's cores
         dt, lab_cpu = time_cpu(mode, ([k.clone() for k in hc[0]], hc[1]), n_samp)
