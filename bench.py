@@ -544,6 +544,9 @@ def main():
             modes[m] = {"value": miv * (K_DELTA - 1) * world / (mms / 1e3), "unit": "frames/s", "achieved_gbs": mach,
                         "frac": mach / peak, "algorithmic_bytes_per_interval": algorithmic_bytes(m),
                         "us_per_interval": mms * 1e3 / miv}
+            if rank == 0 and world == 1 and not args.no_cpu and m in ("linear", "block", "dense_smooth"):
+                dt_st, _ = time_stock_torch(m, mclips[0], device, 6)
+                modes[m]["stock_torch_cuda_us_per_interval"] = dt_st * 1e6 / 6
             del mclips
             torch.cuda.empty_cache()
         out["other_modes"] = modes
