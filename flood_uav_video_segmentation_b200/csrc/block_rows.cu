@@ -91,6 +91,9 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
         // slot now (cp.async, no registers held) and consume it AFTER frames 1..n-1 — the counts are sums over
         // (frame p, frame p-1) pairs, so their order is free.  (Consumed first, its load latency was the top stall.)
         float* kslot = key_stage + static_cast<size_t>(tid) * (CT * 4);
+        // same for the previous interval's last label map (target of frame 0): loaded here, used at the very end
+        const bool have_tc = COUNTS && tc_prev != nullptr;
+        const unsigned tc_word = have_tc ? PixIO<2>::load_labels(tc_prev + pix) : 0u;
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
           const unsigned dsts = static_cast<unsigned>(__cvta_generic_to_shared(kslot + c * 4));
@@ -98,13 +101,52 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
 
-        int lab1[4] = {0, 0, 0, 0}, last[4] = {0, 0, 0, 0};
+        // Labels live as packed float indices {pixel 0, pixel 1}, {pixel 2, pixel 3} (pix4.cuh): the arg-max of a
+        // frame without NaN runs in the float domain, a frame with NaN / Inf takes the exact scan and converts.
+        const u64 magic2 = pack2(8388608.f, 8388608.f);
+        const u64 fw2 = pack2(static_cast<float>(FC::FW), static_cast<float>(FC::FW));
+        auto fields = [&](const u64 (&idx)[2], unsigned (&fld)[4]) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float ml, mh;
+            unpack2(fma2_rn(idx[h], fw2, magic2), ml, mh);
+            fld[2 * h] = one_shl_wrap(__float_as_uint(ml));
+            fld[2 * h + 1] = one_shl_wrap(__float_as_uint(mh));
+          }
+        };
+        // pair (output frame idx, target frame tgt): O += fields(idx), T += s_tgt, I += fields(idx) where equal
+        auto count_pair = [&](const u64 (&idx)[2], const unsigned (&fld)[4], const u64 (&tgt)[2], unsigned s_tgt) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float il, ih, tl, th;
+            unpack2(idx[h], il, ih);
+            unpack2(tgt[h], tl, th);
+            cnt.accI += (il == tl) ? fld[2 * h] : 0u;
+            cnt.accI += (ih == th) ? fld[2 * h + 1] : 0u;
+          }
+          cnt.accO += (fld[0] + fld[1]) + (fld[2] + fld[3]);
+          cnt.accT += s_tgt;
+        };
+        auto exact_scan = [&](const u64 (&xp)[2][CT], u64 (&idx)[2]) {
+          float x[CT][4];
+#pragma unroll
+          for (int c = 0; c < CT; ++c) {
+            unpack2(xp[0][c], x[c][0], x[c][1]);
+            unpack2(xp[1][c], x[c][2], x[c][3]);
+          }
+          int lab[4];
+          argmaxN<CT, 4, true>(x, lab);
+          idx[0] = pack2(static_cast<float>(lab[0]), static_cast<float>(lab[1]));
+          idx[1] = pack2(static_cast<float>(lab[2]), static_cast<float>(lab[3]));
+        };
+        u64 idx1[2] = {0ull, 0ull}, last[2] = {0ull, 0ull};
+        unsigned s_last = 0u;
         int since_spill = 2;
         for (int p = 1; p < n; ++p) {
           const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
           const float* hsL = br_hs + static_cast<size_t>(((p - 1) * 2 + 0) * 2) * CT * XW + xx;
           const float* hsR = br_hs + static_cast<size_t>(((p - 1) * 2 + 1) * 2) * CT * XW + xx;
-          float x[CT][4];
+          u64 xp[2][CT];
           u64 probe = zero2;
 #pragma unroll
           for (int c = 0; c < CT; ++c) {
@@ -116,61 +158,82 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
             const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(hsR + (1 * CT + c) * XW);
             const u64 fa = two_term2<Nm::kUpOuter>(hl0, f0.x, hl1, f1.x, one2), fb = two_term2<Nm::kUpOuter>(hl0, f0.y, hl1, f1.y, one2);
             const u64 ba = two_term2<Nm::kUpOuter>(hl0, b0.x, hl1, b1.x, one2), bb = two_term2<Nm::kUpOuter>(hl0, b0.y, hl1, b1.y, one2);
-            const u64 va = blend2x2(w0, fa, w1, ba, one2), vb = blend2x2(w0, fb, w1, bb, one2);
-            probe = fma2_rn(va, zero2, probe);
-            probe = fma2_rn(vb, zero2, probe);
-            unpack2(va, x[c][0], x[c][1]);
-            unpack2(vb, x[c][2], x[c][3]);
-            if (LOGITS) PixIO<2>::store(logits + (static_cast<long long>(p) * CT + c) * HW + pix, x[c]);
+            xp[0][c] = blend2x2(w0, fa, w1, ba, one2);
+            xp[1][c] = blend2x2(w0, fb, w1, bb, one2);
+            probe = fma2_rn(xp[0][c], zero2, probe);
+            probe = fma2_rn(xp[1][c], zero2, probe);
+            if (LOGITS) {
+              float xs[4];
+              unpack2(xp[0][c], xs[0], xs[1]);
+              unpack2(xp[1][c], xs[2], xs[3]);
+              PixIO<2>::store(logits + (static_cast<long long>(p) * CT + c) * HW + pix, xs);
+            }
           }
           float pr0, pr1;
           unpack2(probe, pr0, pr1);
-          int lab[4];
-          if ((pr0 == pr0) && (pr1 == pr1)) argmaxN<CT, 4, false>(x, lab);     // x*0 is NaN iff x is Inf/NaN
-          else argmaxN<CT, 4, true>(x, lab);
-          if (labels) PixIO<2>::store_labels(labels + static_cast<long long>(p) * HW + pix, lab);
+          u64 idx[2];
+          if ((pr0 == pr0) && (pr1 == pr1)) {          // x*0 is NaN iff x is Inf/NaN
+            idx[0] = argmax2f<CT>(xp[0]);
+            idx[1] = argmax2f<CT>(xp[1]);
+          } else {
+            exact_scan(xp, idx);
+          }
+          if (labels) PixIO<2>::store_label_word(labels + static_cast<long long>(p) * HW + pix, PixIO<2>::label_word(idx));
           if (COUNTS) {
+            unsigned fld[4];
+            fields(idx, fld);
             if (p == 1) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) lab1[i] = lab[i];
+              idx1[0] = idx[0];
+              idx1[1] = idx[1];
             } else {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) cnt.add(lab[i], FieldCounts<CT>::field(lab[i]), last[i], FieldCounts<CT>::field(last[i]));
+              count_pair(idx, fld, last, s_last);
               if (++since_spill >= FC::CAP / 4) {
                 cnt.spill();
                 since_spill = 0;
               }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) last[i] = lab[i];
+            s_last = (fld[0] + fld[1]) + (fld[2] + fld[3]);
+            last[0] = idx[0];
+            last[1] = idx[1];
           }
         }
         // frame 0: the key frame itself (flow/model.py:195-197), then the pairs (0, previous interval) and (1, 0)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (COUNTS && 4 * since_spill + 8 > FC::CAP) cnt.spill();       // room for the two pairs below
         {
-          float x[CT][4];
+          u64 xp[2][CT];
 #pragma unroll
           for (int c = 0; c < CT; ++c) {
             const float4 v = *reinterpret_cast<const float4*>(kslot + c * 4);
-            x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
-            if (LOGITS) PixIO<2>::store(logits + c * HW + pix, x[c]);
+            xp[0][c] = pack2(v.x, v.y);
+            xp[1][c] = pack2(v.z, v.w);
+            if (LOGITS) {
+              const float xs[4] = {v.x, v.y, v.z, v.w};
+              PixIO<2>::store(logits + c * HW + pix, xs);
+            }
           }
-          int lab[4];
-          argmaxN<CT, 4, true>(x, lab);
-          if (labels) PixIO<2>::store_labels(labels + pix, lab);
+          u64 idx0[2];
+          exact_scan(xp, idx0);
+          const unsigned w = PixIO<2>::label_word(idx0);
+          if (labels) PixIO<2>::store_label_word(labels + pix, w);
           if (COUNTS) {
-            if (tc_prev != nullptr) {
-              const unsigned t = PixIO<2>::load_labels(tc_prev + pix);
+            unsigned fld0[4];
+            fields(idx0, fld0);
+            if (have_tc) {
+              const unsigned t = tc_word;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const int tl = (t >> (8 * i)) & 255u;
+                const int tl = (t >> (8 * i)) & 255u, lab = (w >> (8 * i)) & 255u;
                 const unsigned ft = (tl < CT) ? FieldCounts<CT>::field(tl) : 0u;
-                const unsigned fo = (tl == ignore_index) ? 0u : FieldCounts<CT>::field(lab[i]);
-                cnt.add(lab[i], fo, tl, ft);
+                const unsigned fo = (tl == ignore_index) ? 0u : fld0[i];
+                cnt.add(lab, fo, tl, ft);
               }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cnt.add(lab1[i], FieldCounts<CT>::field(lab1[i]), lab[i], FieldCounts<CT>::field(lab[i]));
+            if (n > 1) {
+              unsigned fld1[4];
+              fields(idx1, fld1);
+              count_pair(idx1, fld1, idx0, (fld0[0] + fld0[1]) + (fld0[2] + fld0[3]));
+            }
           }
         }
         if (COUNTS) cnt.spill();

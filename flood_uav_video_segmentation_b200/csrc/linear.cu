@@ -117,11 +117,117 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 template <int CT, int NP, bool COUNTS, bool NANSAFE, bool LOGITS = true>
 __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 (&b)[CT][NP], long long HW,
                                               long long pix, int n, uint8_t* __restrict__ labels,
-                                              float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
+                                              float* __restrict__ logits, bool have_tc, unsigned tc_word,
                                               int ignore_index, const BlendWeights& wts, u64 one2,
                                               FieldCounts<CT>& cnt) {
   using FC = FieldCfg<CT>;
   constexpr int NPX = 2 * NP;
+  if constexpr (!NANSAFE) {
+    // ---- no value can be NaN: arg-max, counter fields and label bytes in the float domain (pix4.cuh)
+    static_assert(CT >= 2 && CT <= 64 && FC::FW * (CT - 1) < 32, "float-domain index packing");
+    const u64 magic2 = pack2(8388608.f, 8388608.f);                              // 2^23
+    const u64 fw2 = pack2(static_cast<float>(FC::FW), static_cast<float>(FC::FW));
+    u64 last[NP];                      // float indices of the previous frame
+    unsigned s_prev = 0u;              // sum of its counter fields: the T term of the next frame in one add
+    // counter fields of NPX labels: fld[i] = 1 << (FW * idx_i)
+    auto fields = [&](const u64 (&idx)[NP], unsigned (&fld)[NPX]) {
+#pragma unroll
+      for (int h = 0; h < NP; ++h) {
+        float ml, mh;
+        unpack2(fma2_rn(idx[h], fw2, magic2), ml, mh);
+        fld[2 * h] = one_shl_wrap(__float_as_uint(ml));
+        fld[2 * h + 1] = one_shl_wrap(__float_as_uint(mh));
+      }
+    };
+    // ---- frame 0: the unblended key frame (flow/model.py:195-197)
+    {
+      u64 idx[NP];
+#pragma unroll
+      for (int h = 0; h < NP; ++h) {
+        u64 x[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) x[c] = a[c][h];
+        idx[h] = argmax2f<CT>(x);
+      }
+      if (LOGITS && logits) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          float x[NPX];
+#pragma unroll
+          for (int h = 0; h < NP; ++h) unpack2(a[c][h], x[2 * h], x[2 * h + 1]);
+          PixIO<NP>::store(logits + c * HW + pix, x);
+        }
+      }
+      const unsigned w = PixIO<NP>::label_word(idx);
+      if (labels) PixIO<NP>::store_label_word(labels + pix, w);
+      if (COUNTS) {
+        unsigned fld[NPX];
+        fields(idx, fld);
+        if (have_tc) {                      // tc_word: the callers load it long before it is needed (a DRAM round trip)
+#pragma unroll
+          for (int i = 0; i < NPX; ++i) {
+            const int tl = (tc_word >> (8 * i)) & 255u, lab = (w >> (8 * i)) & 255u;
+            const unsigned ft = (tl < CT) ? FieldCounts<CT>::field(tl) : 0u;
+            // output[target == ignore] = ignore, and ignore is outside [0,CT) on this path: nothing of this pixel counts
+            const unsigned fo = (tl == ignore_index) ? 0u : fld[i];
+            cnt.add(lab, fo, tl, ft);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) s_prev += fld[i];
+#pragma unroll
+        for (int h = 0; h < NP; ++h) last[h] = idx[h];
+      }
+    }
+    // ---- frames 1..n-1: fl(fl(w0*a) + fl(w1*b))  (flow/model.py:233-237)
+    int since_spill = 1;
+    for (int p = 1; p < n; ++p) {
+      const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
+      float* lg = (LOGITS && logits) ? logits + (static_cast<long long>(p) * CT) * HW + pix : nullptr;
+      u64 idx[NP];
+      u64 x[NP][CT];
+#pragma unroll
+      for (int h = 0; h < NP; ++h) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) x[h][c] = blend2x2(w0, a[c][h], w1, b[c][h], one2);
+        idx[h] = argmax2f<CT>(x[h]);
+      }
+      if (LOGITS && lg) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          float xs[NPX];
+#pragma unroll
+          for (int h = 0; h < NP; ++h) unpack2(x[h][c], xs[2 * h], xs[2 * h + 1]);
+          PixIO<NP>::store(lg + c * HW, xs);
+        }
+      }
+      if (labels) PixIO<NP>::store_label_word(labels + static_cast<long long>(p) * HW + pix, PixIO<NP>::label_word(idx));
+      if (COUNTS) {
+        unsigned fld[NPX];
+        fields(idx, fld);
+        unsigned s_cur = 0u;
+#pragma unroll
+        for (int h = 0; h < NP; ++h) {
+          float il, ih, ll, lh;
+          unpack2(idx[h], il, ih);
+          unpack2(last[h], ll, lh);
+          cnt.accI += (il == ll) ? fld[2 * h] : 0u;
+          cnt.accI += (ih == lh) ? fld[2 * h + 1] : 0u;
+          s_cur += fld[2 * h] + fld[2 * h + 1];
+          last[h] = idx[h];
+        }
+        cnt.accO += s_cur;               // this frame as the output ...
+        cnt.accT += s_prev;              // ... against the previous frame as the target (flow/base.py:280-295)
+        s_prev = s_cur;
+        if (++since_spill >= FC::CAP / NPX) {
+          cnt.spill();
+          since_spill = 0;
+        }
+      }
+    }
+    if (COUNTS) cnt.spill();
+    return;
+  }
   int last[NPX];
   // ---- frame 0: the unblended key frame (flow/model.py:195-197)
   {
@@ -136,8 +242,8 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
     argmaxN<CT, NPX, NANSAFE>(x, lab);
     if (labels) PixIO<NP>::store_labels(labels + pix, lab);
     if (COUNTS) {
-      if (tc_prev != nullptr) {
-        const unsigned t = PixIO<NP>::load_labels(tc_prev + pix);
+      if (have_tc) {                      // tc_word: the callers load it long before it is needed (a DRAM round trip)
+        const unsigned t = tc_word;
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
           const int tl = (t >> (8 * i)) & 255u;
@@ -202,6 +308,8 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const long long pix = v * NPX;
     u64 a[CT][NP], b[CT][NP];
+    const bool have_tc = COUNTS && tc_prev != nullptr;
+    const unsigned tc_word = have_tc ? PixIO<NP>::load_labels(tc_prev + pix) : 0u;
 #pragma unroll
     for (int c = 0; c < CT; ++c) PixIO<NP>::load(prev + c * HW + pix, a[c]);
     if (n > 1) {
@@ -227,9 +335,9 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
     float pr0, pr1;
     unpack2(probe, pr0, pr1);
     if ((pr0 == pr0) && (pr1 == pr1))
-      linear_frames<CT, NP, COUNTS, false>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      linear_frames<CT, NP, COUNTS, false>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
     else
-      linear_frames<CT, NP, COUNTS, true>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+      linear_frames<CT, NP, COUNTS, true>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
   }
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
@@ -318,9 +426,19 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
 
   FieldCounts<CT> cnt;
   cnt.init();
+  // previous interval's last label map (temporal-consistency target of frame 0): 4 labels per thread and tile, loaded
+  // one tile ahead — consumed straight after a load it stalled every warp for a DRAM round trip per tile
+  // (long-scoreboard 2.2 warps per issue, profiles/r01_ncu_linear_final.txt)
+  const bool have_tc = COUNTS && tc_prev != nullptr;
+  auto tc_load = [&](long long tile) -> unsigned {
+    const long long px = tile * BULK_TILE + tid * 4;
+    return (have_tc && px < HW) ? __ldg(reinterpret_cast<const unsigned*>(tc_prev + px)) : 0u;
+  };
+  unsigned tc_word = tc_load(blockIdx.x);
   for (long long i = 0;; ++i) {
     const long long t = blockIdx.x + i * gridDim.x;
     if (t >= ntiles) break;
+    const unsigned tc_next = tc_load(t + gridDim.x);
     const int s = static_cast<int>(i % BULK_STAGES);
     lin_wait(lin_smem_u32(&bars[s]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
     const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * 4;
@@ -365,10 +483,11 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
       float pr0, pr1;
       unpack2(probe, pr0, pr1);
       if ((pr0 == pr0) && (pr1 == pr1))
-        linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+        linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
       else
-        linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+        linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
     }
+    tc_word = tc_next;
   }
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
@@ -456,6 +575,9 @@ linear_lowres_kernel(const float* __restrict__ prev_lr, const float* __restrict_
       const u64 hl0 = pack2(hc.l0, hc.l0), hl1 = pack2(hc.l1, hc.l1);
       for (int xx = tid * 4; xx < xw; xx += LR_THREADS * 4) {
         u64 a[CT][2], b[CT][2];
+        const long long pix = static_cast<long long>(y) * W + x0 + xx;
+        const bool have_tc = COUNTS && tc_prev != nullptr;
+        const unsigned tc_word = have_tc ? __ldg(reinterpret_cast<const unsigned*>(tc_prev + pix)) : 0u;
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
           const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(lr_hs + ((0 * 2 + 0) * CT + c) * XW + xx);
@@ -482,11 +604,10 @@ linear_lowres_kernel(const float* __restrict__ prev_lr, const float* __restrict_
         }
         float pr0, pr1;
         unpack2(probe, pr0, pr1);
-        const long long pix = static_cast<long long>(y) * W + x0 + xx;
         if ((pr0 == pr0) && (pr1 == pr1))
-          linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+          linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
         else
-          linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, tc_prev, ignore_index, wts, one2, cnt);
+          linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
       }
     }
   }

@@ -100,6 +100,114 @@ confusion_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long long
   }
 }
 
+template <typename K>
+static int persistent_grid(K kernel, long long work_items, int threads) {
+  const long long need = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count()) * blocks_per_sm(kernel, threads);
+  long long g = need < cap ? need : cap;
+  return static_cast<int>(g > 0 ? g : 1);
+}
+
+// ---------------------------------------------------------------------------
+// Fast path of fuvs_confusion: torch.histc binning, 2 <= K <= 5, ignore_index outside [0,K) (the reference's GPU
+// metric at its class counts, util/util.py:52-63).  The general kernel above reduces across the warp after every 4
+// labels and loads one label per instruction: 40 us for 5 x 1080p whatever the dtypes (tools/metric_bench.py), i.e.
+// issue-bound at 35 % of the HBM roofline for uint8 predictions against int64 targets.  Here a thread takes 16 labels
+// per iteration with 128-bit loads, counts in three 32-bit registers with 6/8-bit class fields (FieldCounts) and the
+// warp reduction happens once per kernel.
+// ---------------------------------------------------------------------------
+template <typename T> struct Lab16;
+template <> struct Lab16<uint8_t> {
+  uint4 w;
+  __device__ __forceinline__ void load(const uint8_t* p, bool stream) {
+    w = stream ? __ldcs(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
+  }
+  __device__ __forceinline__ long long get(int i) const {
+    const unsigned word = i < 4 ? w.x : i < 8 ? w.y : i < 12 ? w.z : w.w;
+    return (word >> (8 * (i & 3))) & 255u;
+  }
+  __device__ __forceinline__ void set(int i, long long v) {
+    unsigned& word = i < 4 ? w.x : i < 8 ? w.y : i < 12 ? w.z : w.w;
+    word = (word & ~(255u << (8 * (i & 3)))) | ((static_cast<unsigned>(v) & 255u) << (8 * (i & 3)));
+  }
+  __device__ __forceinline__ void store(uint8_t* p) const { *reinterpret_cast<uint4*>(p) = w; }
+};
+template <> struct Lab16<long long> {
+  longlong2 w[8];
+  __device__ __forceinline__ void load(const long long* p, bool stream) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      w[k] = stream ? __ldcs(reinterpret_cast<const longlong2*>(p) + k) : reinterpret_cast<const longlong2*>(p)[k];
+  }
+  __device__ __forceinline__ long long get(int i) const { return (i & 1) ? w[i >> 1].y : w[i >> 1].x; }
+  __device__ __forceinline__ void set(int i, long long v) { if (i & 1) w[i >> 1].y = v; else w[i >> 1].x = v; }
+  __device__ __forceinline__ void store(long long* p) const {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) reinterpret_cast<longlong2*>(p)[k] = w[k];
+  }
+};
+
+template <typename PT, typename TT, int KT>
+__global__ void __launch_bounds__(256)
+confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long long ngroups, long long ignore,
+                     int mutate, unsigned long long* __restrict__ counts) {
+  using FC = FieldCfg<KT>;
+  __shared__ unsigned sh[24];
+  FieldCounts<KT> cnt;
+  cnt.init();
+  int since_spill = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    Lab16<PT> o;
+    Lab16<TT> t;
+    o.load(pred + g * 16, mutate == 0);
+    t.load(target + g * 16, true);
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const long long tv = t.get(i);
+      long long ov = o.get(i);
+      if (tv == ignore) {                                   // output[target == ignore] = ignore (util/util.py:57)
+        ov = static_cast<long long>(static_cast<PT>(ignore));
+        if (mutate) { o.set(i, ov); changed = true; }
+      }
+      const unsigned ft = (tv >= 0 && tv < KT) ? FieldCounts<KT>::field(static_cast<int>(tv)) : 0u;
+      const unsigned fo = (ov >= 0 && ov < KT) ? FieldCounts<KT>::field(static_cast<int>(ov)) : 0u;
+      cnt.accO += fo;
+      cnt.accT += ft;
+      cnt.accI += (ov == tv) ? fo : 0u;
+    }
+    if (mutate && changed) o.store(pred + g * 16);
+    since_spill += 16;
+    if (since_spill + 16 > FC::CAP) {
+      cnt.spill();
+      since_spill = 0;
+    }
+  }
+  cnt.finish(sh, counts, KT);
+}
+
+template <typename PT, typename TT>
+static int launch_confusion_v16(void* pred, const void* target, long long ngroups, int K, long long ignore, int mutate,
+                                long long* counts, cudaStream_t st) {
+  auto cu = reinterpret_cast<unsigned long long*>(counts);
+  const int threads = 256;
+#define FUVS_CF16(KT_)                                                                                         \
+  {                                                                                                            \
+    const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_>, ngroups, threads);                     \
+    confusion_v16_kernel<PT, TT, KT_><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
+                                                               ngroups, ignore, mutate, cu);                   \
+  }
+  switch (K) {
+    case 2: FUVS_CF16(2) break;
+    case 3: FUVS_CF16(3) break;
+    case 4: FUVS_CF16(4) break;
+    default: FUVS_CF16(5) break;
+  }
+#undef FUVS_CF16
+  return check_launch("fuvs_confusion(v16)");
+}
+
 template <int VEC, int KT>
 __global__ void __launch_bounds__(256)
 temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
@@ -199,13 +307,6 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
   cnt.finish(sh, counts, KT);
 }
 
-template <typename K>
-static int persistent_grid(K kernel, long long work_items, int threads) {
-  const long long need = (work_items + threads - 1) / threads;
-  const long long cap = static_cast<long long>(sm_count()) * blocks_per_sm(kernel, threads);
-  long long g = need < cap ? need : cap;
-  return static_cast<int>(g > 0 ? g : 1);
-}
 
 int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
                            int ignore_index, long long* counts, cudaStream_t st) {
@@ -261,6 +362,17 @@ static int launch_confusion(void* pred, const void* target, long long N, int K, 
   auto cu = reinterpret_cast<unsigned long long*>(counts);
   const int np_bins = flags & 1, mutate = (flags & FUVS_MUTATE_PRED) ? 1 : 0;
   const int threads = 256;
+  // fast path: histc binning, 2 <= K <= 5, ignore outside the classes, 16-byte aligned label arrays; the
+  // N % 16 tail goes through the general kernel below
+  if (!np_bins && K >= 2 && K <= 5 && (ignore < 0 || ignore >= K) && N >= 16 && aligned16(pred) && aligned16(target)) {
+    const long long ngroups = N / 16;
+    if (int e = launch_confusion_v16<PT, TT>(pred, target, ngroups, K, ignore, mutate, counts, st)) return e;
+    const long long done = ngroups * 16;
+    if (done == N) return FUVS_OK;
+    pred = static_cast<PT*>(pred) + done;
+    target = static_cast<const TT*>(target) + done;
+    N -= done;
+  }
   if (K <= 8) {
     const int grid = persistent_grid(confusion_kernel<PT, TT, true>, (N + 3) / 4, threads);
     confusion_kernel<PT, TT, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), N,

@@ -32,6 +32,57 @@ __device__ __forceinline__ void argmaxN(const float (&x)[CT][NPX], int (&lab)[NP
   }
 }
 
+// ---------------------------------------------------------------------------
+// Arg-max in the float domain for values that cannot be NaN (the fast path of the streaming kernels).
+// The compare-select scan above costs 3 instructions per class and pixel on the ALU pipe (FSETP, FSEL, SEL), 12 per
+// pixel at C = 5, in one dependent chain — the bound of the linear kernel (profiles/r01_ncu_linear_final.txt).  Here
+//   m   = max over classes                      2 FMNMX3 at C = 5 (Blackwell three-input min/max; +0 > -0)
+//   n_c = (x_c != m) ? 1.0f : 0.0f              1 FSET per class, independent of each other
+//   idx = n_0 (1 + n_1 (1 + n_2 (1 + ...)))     = number of leading classes that differ from the maximum
+//                                               = lowest index that attains it: torch.max's tie rule, -0 == +0
+// and the Horner chain t <- fma(n_c, t, n_c) runs on packed FP32x2 for a pixel pair (FMA pipe, exact small
+// integers).  6 ALU + 1.5 FMA-pipe instructions per pixel instead of 12 ALU.  The index stays a float: it is
+// compared as a float, turned into a counter field with one FFMA2 (FW * idx + 2^23: the low mantissa bits are the
+// shift amount) and packed into label bytes the same way.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int CT>
+__device__ __forceinline__ float max_classes(const float (&v)[CT]) {
+  float m = v[0];
+  int c = 1;
+#pragma unroll
+  for (; c + 1 < CT; c += 2) m = fmax3(m, v[c], v[c + 1]);
+  if (c < CT) m = fmaxf(m, v[c]);
+  return m;
+}
+__device__ __forceinline__ float differs(float a, float b) { return a != b ? 1.0f : 0.0f; }
+
+// {float index of pixel 0, float index of pixel 1} of the first maximum over CT packed class values (CT >= 2)
+template <int CT>
+__device__ __forceinline__ u64 argmax2f(const u64 (&x)[CT]) {
+  float lo[CT], hi[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) unpack2(x[c], lo[c], hi[c]);
+  const float mlo = max_classes<CT>(lo), mhi = max_classes<CT>(hi);
+  u64 t = pack2(differs(lo[CT - 2], mlo), differs(hi[CT - 2], mhi));
+#pragma unroll
+  for (int c = CT - 3; c >= 0; --c) {
+    const u64 nc = pack2(differs(lo[c], mlo), differs(hi[c], mhi));
+    t = fma2_rn(nc, t, nc);
+  }
+  return t;
+}
+// 1 << (low 5 bits of c): a float index biased by 2^23 carries its integer in the low mantissa bits
+__device__ __forceinline__ unsigned one_shl_wrap(unsigned c) {
+  unsigned d;
+  asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(c));
+  return d;
+}
+
 // NP pixel pairs per thread: NP = 2 -> 4 pixels (128-bit loads, 32-bit label stores),
 //                            NP = 1 -> 2 pixels (64-bit loads, 16-bit label stores; half the registers, twice the warps)
 template <int NP> struct PixIO;
@@ -48,6 +99,15 @@ template <> struct PixIO<2> {
     *reinterpret_cast<unsigned*>(p) = (unsigned)l[0] | ((unsigned)l[1] << 8) | ((unsigned)l[2] << 16) | ((unsigned)l[3] << 24);
   }
   static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+  // label bytes of 4 pixels from the packed float indices {i0,i1}, {i2,i3}: {i0 + 65536 i2, i1 + 65536 i3} + 2^23, then
+  // one byte permute of the two mantissas
+  static __device__ __forceinline__ unsigned label_word(const u64 (&idx)[2]) {
+    const u64 r = fma2_rn(idx[1], pack2(65536.f, 65536.f), fma2_rn(idx[0], pack2(1.f, 1.f), pack2(8388608.f, 8388608.f)));
+    float rl, rh;
+    unpack2(r, rl, rh);
+    return __byte_perm(__float_as_uint(rl), __float_as_uint(rh), 0x6240);
+  }
+  static __device__ __forceinline__ void store_label_word(uint8_t* p, unsigned w) { *reinterpret_cast<unsigned*>(p) = w; }
 };
 template <> struct PixIO<1> {
   static __device__ __forceinline__ void load(const float* p, u64 (&d)[1]) {
@@ -61,6 +121,15 @@ template <> struct PixIO<1> {
     *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>((unsigned)l[0] | ((unsigned)l[1] << 8));
   }
   static __device__ __forceinline__ unsigned load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned short*>(p)); }
+  static __device__ __forceinline__ unsigned label_word(const u64 (&idx)[1]) {
+    const u64 r = fma2_rn(idx[0], pack2(1.f, 1.f), pack2(8388608.f, 8388608.f));
+    float rl, rh;
+    unpack2(r, rl, rh);
+    return __byte_perm(__float_as_uint(rl), __float_as_uint(rh), 0x0040) & 0xffffu;
+  }
+  static __device__ __forceinline__ void store_label_word(uint8_t* p, unsigned w) {
+    *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>(w);
+  }
 };
 
 }  // namespace fuvs

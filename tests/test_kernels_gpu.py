@@ -215,6 +215,11 @@ def test_argmax_ties_and_nan(cuda):
     x[0, :, 0, 2] = torch.tensor([-0.0, 0.0, -0.0, 0.0, -0.0])          # -0 == +0 -> index 0
     x[0, :, 0, 3] = torch.tensor([float("-inf")] * 5)
     x[0, :, 0, 4] = torch.tensor([0.0, float("inf"), float("inf"), 1.0, 2.0])
+    # pixels 8..11 share a thread with no NaN / Inf in it: the float-domain arg-max of the fast path (pix4.cuh)
+    x[0, :, 0, 8] = torch.tensor([-0.0, 0.0, -0.0, 0.0, -0.0])          # -0 == +0 -> index 0
+    x[0, :, 0, 9] = torch.tensor([-1.0, -0.0, 0.0, -2.0, 0.0])          # -> index 1
+    x[0, :, 0, 10] = torch.tensor([-3.0, -2.0, -1.0, -0.5, 7.0])        # last class
+    x[0, :, 0, 11] = torch.tensor([1e-45, 1e-45, 0.0, -1e-45, 1e-45])   # denormal ties
     x[0, :, 1:, :] = torch.randn(C, H - 1, W, generator=torch.Generator().manual_seed(3)).round()  # many ties
     xc = x.to(cuda)
     ref = xc.max(1)[1]
@@ -302,6 +307,34 @@ def test_confusion_vs_oracle(cuda, K, pdt, tdt):
         o2 = pred.to(cuda).clone()
         ri, ru, rt = mo.intersection_and_union_torch(o2, target.to(cuda), K, 255)
         assert np.array_equal(got, torch.stack([ri, ru, rt]).cpu().numpy().astype(np.int64))
+
+
+@pytest.mark.parametrize("K", [2, 3, 4, 5])
+@pytest.mark.parametrize("pdt,tdt", [(torch.int64, torch.int64), (torch.uint8, torch.int64), (torch.uint8, torch.uint8),
+                                     (torch.int64, torch.uint8)])
+def test_confusion_fast_path_edges(cuda, K, pdt, tdt):
+    """16-labels-per-thread path of fuvs_confusion (histc binning, 2 <= K <= 5): predictions outside [0, K) (negative
+    for int64), targets K..K+2 and 255, a length that leaves a tail, views that start off a 16-byte boundary (general
+    kernel), accumulation over calls, with and without the in-place ignore substitution."""
+    N = 16 * 4099 + 7
+    g = torch.Generator().manual_seed(100 + K)
+    lo = -2 if pdt == torch.int64 else 0
+    pred = torch.randint(lo, K + 2, (N + 3,), generator=g).to(pdt)
+    target = torch.randint(0, K + 3, (N + 3,), generator=g)
+    target[torch.rand(N + 3, generator=g) < 0.07] = 255
+    target = target.to(tdt)
+    counts = kernels.new_counts(K, cuda)
+    tot = np.zeros((3, K), np.int64)
+    for off, mutate in ((0, False), (0, True), (3, True), (1, False)):
+        p, t = pred[off:off + N], target[off:off + N]
+        pc, tc = pred.to(cuda)[off:off + N], target.to(cuda)[off:off + N]
+        kernels.confusion(pc, tc, K, 255, counts=counts, mutate_pred=mutate)
+        tot += np.stack(mo.intersection_and_union_histc_ints(p.numpy(), t.numpy(), K, 255))
+        exp = p.clone()
+        if mutate:
+            exp[t == 255] = 255
+        assert torch.equal(pc.cpu(), exp)
+        assert np.array_equal(counts.cpu().numpy(), tot)
 
 
 def test_confusion_accumulates_and_ragged(cuda):
