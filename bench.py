@@ -193,20 +193,57 @@ def time_resident(kernels, dist_mod, mode, clips, steps, warmup, clips_per_step,
     run_interval.scratch = torch.empty((need,), dtype=torch.float32, device=device)
     ci = 0
 
-    def step():
+    def eager_step():
         nonlocal ci
         for _ in range(clips_per_step):
             run_clip(kernels, mode, clips[ci % len(clips)], counts)
             ci += 1
 
     for _ in range(warmup):
-        step()
+        eager_step()
+    # A step is a fixed sequence of C-ABI calls on fixed buffers: capture it once per phase of the clip cycle in a CUDA
+    # graph and replay it, so the timed region measures the GPU and not the Python/ctypes call overhead (~20 us per
+    # interval, the same order as a linear-mode interval).  FUVS_BENCH_GRAPH=0 times eager launches instead.
+    time_resident.launch = "eager"
+    step = eager_step
+    if os.environ.get("FUVS_BENCH_GRAPH", "1") != "0":
+        try:
+            import math
+            nphase = (len(clips) * clips_per_step // math.gcd(len(clips), clips_per_step)) // clips_per_step
+            torch.cuda.synchronize(device)
+            graphs, per_graph = [], []
+            ci = 0
+            for _ in range(nphase):
+                g = torch.cuda.CUDAGraph()
+                l_before = launch_count()
+                with torch.cuda.graph(g):
+                    eager_step()
+                per_graph.append(launch_count() - l_before)
+                graphs.append(g)
+            phase = 0
+
+            def graph_step():
+                nonlocal phase
+                graphs[phase % nphase].replay()
+                time_resident.replayed += per_graph[phase % nphase]
+                phase += 1
+
+            step = graph_step
+            time_resident.launch = "cuda_graph"
+            for _ in range(2):
+                step()
+        except Exception as exc:          # capture refused: fall back to eager launches and say so
+            print(f"[bench] CUDA graph capture failed ({exc!r}); timing eager launches", file=sys.stderr)
+            torch.cuda.synchronize(device)
+            step = eager_step
+            time_resident.launch = "eager"
     counts.zero_()
     torch.cuda.synchronize(device)
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize(device)
     l0 = launch_count()
+    time_resident.replayed = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx = sampler if sampler is not None else _Null()
     with ctx:
@@ -219,12 +256,16 @@ def time_resident(kernels, dist_mod, mode, clips, steps, warmup, clips_per_step,
     if world > 1:
         torch.distributed.barrier()
     ms = e0.elapsed_time(e1)
-    launches = launch_count() - l0
+    launches = launch_count() - l0 + time_resident.replayed        # kernels replayed from the graphs count like launches
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms = float(t.item())
     return ms, launches, counts
+
+
+time_resident.launch = "eager"
+time_resident.replayed = 0
 
 
 class _Null:
@@ -519,6 +560,8 @@ def main():
     sampler = ClockSampler(local)
     ms, launches, counts = time_resident(kernels, fdist, mode, clips, args.steps, args.warmup, args.clips_per_step,
                                          device, world, sampler)
+    config["launch"] = ("one CUDA graph replay per step (captured C-ABI calls)" if time_resident.launch == "cuda_graph"
+                        else "eager C-ABI calls from Python")
     intervals = args.steps * args.clips_per_step * 3
     frames = intervals * (K_DELTA - 1)
     value = frames * world / (ms / 1e3)

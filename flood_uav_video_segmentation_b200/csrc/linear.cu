@@ -354,6 +354,7 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
 constexpr int BULK_THREADS = 512;
 constexpr int BULK_TILE = BULK_THREADS * 4;        // pixels per tile
 constexpr int BULK_STAGES = 2;
+constexpr int BULK_NQ_MAX = 4;                     // independent slice pipelines per CTA (NQ = 4: 4 warps, 512 pixels each)
 
 __device__ __forceinline__ uint32_t lin_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ bool lin_try_wait(uint32_t bar, uint32_t parity) {
@@ -373,54 +374,66 @@ __device__ __forceinline__ void lin_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-template <int CT, bool COUNTS, bool LOGITS>
+// BULK_NQ slice pipelines per CTA: slice q = warps (16/NQ) q .. owns pixels [2048/NQ q, ...) of every tile, with its own
+// mbarrier per stage and its own release counter.  NQ = 1 (one barrier per stage, 8 KB bulk copies) is the default;
+// NQ = 4 lets a quarter start when its own 20 KB have landed and refill as soon as its four warps hold their operands,
+// but its 2 KB bulk copies cost more than the decoupling gains: 24.0 vs 22.5 us per interval (FUVS_LINEAR_NQ=4 keeps
+// the variant reachable for re-measurement).
+template <int CT, bool COUNTS, bool LOGITS, int BULK_NQ>
 __global__ void __launch_bounds__(BULK_THREADS, 1)
 linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __restrict__ next,
                                 long long HW, int n,
                                 uint8_t* __restrict__ labels, float* __restrict__ logits,
                                 const uint8_t* __restrict__ tc_prev,
                                 unsigned long long* __restrict__ counts, int ignore_index,
-                                const BlendWeights wts, float one) {
+                                const BlendWeights wts, float one, int pdl) {
   extern __shared__ __align__(128) unsigned char lin_smem[];
   __shared__ unsigned sh[24];
-  constexpr int NW = BULK_THREADS / 32;
+  constexpr int BULK_QPX = BULK_TILE / BULK_NQ;
+  constexpr int BULK_QWARPS = BULK_THREADS / 32 / BULK_NQ;
   const int nplanes = (n > 1) ? 2 * CT : CT;
   float* stage_base = reinterpret_cast<float*>(lin_smem);                               // [STAGES][2*CT][BULK_TILE]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(lin_smem + static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4);
-  unsigned* done = reinterpret_cast<unsigned*>(bars + BULK_STAGES);
+  unsigned* done = reinterpret_cast<unsigned*>(bars + BULK_STAGES * BULK_NQ);           // [STAGES][NQ]
   const int tid = threadIdx.x, lane = tid & 31;
+  const int q = tid / (BULK_QPX / 4);                                                   // this thread's quarter
   const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
   const u64 one2 = pack2(one, one);
   const float zero = __fsub_rn(one, one);
   const u64 zero2 = pack2(zero, zero);
 
   if (tid == 0) {
-    for (int s = 0; s < BULK_STAGES; ++s) {
+    for (int s = 0; s < BULK_STAGES * BULK_NQ; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lin_smem_u32(&bars[s])), "r"(1) : "memory");
       done[s] = 0u;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream drains
+  // (its CTAs take an SM as soon as one is free); nothing in global memory is touched before the wait
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // one thread: stream the channel rows of this CTA's i-th tile into stage i % STAGES
+  // one thread of quarter q: stream the channel rows of the quarter's slice of this CTA's i-th tile into stage i % STAGES
   auto issue = [&](long long i) {
     const long long t = blockIdx.x + i * gridDim.x;
     if (t >= ntiles) return;
     const int s = static_cast<int>(i % BULK_STAGES);
-    const long long pix0 = t * BULK_TILE;
+    const long long pix0 = t * BULK_TILE + q * BULK_QPX;
     const long long rem = HW - pix0;
-    const unsigned bytes = static_cast<unsigned>((rem < BULK_TILE ? rem : BULK_TILE) * 4);     // multiple of 16: HW % 4 == 0
-    const uint32_t bar = lin_smem_u32(&bars[s]);
+    if (rem <= 0) return;                                                                      // nobody waits for it
+    const unsigned bytes = static_cast<unsigned>((rem < BULK_QPX ? rem : BULK_QPX) * 4);     // multiple of 16: HW % 4 == 0
+    const uint32_t bar = lin_smem_u32(&bars[s * BULK_NQ + q]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * nplanes) : "memory");
-    float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE;
+    float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + q * BULK_QPX;
     for (int p = 0; p < nplanes; ++p) {
       const float* g = (p < CT ? prev + p * HW : next + (p - CT) * HW) + pix0;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(lin_smem_u32(sb + static_cast<size_t>(p) * BULK_TILE)), "l"(g), "r"(bytes), "r"(bar) : "memory");
     }
   };
-  if (tid == 0) {
+  if ((tid & (BULK_QPX / 4 - 1)) == 0) {
     for (int i = 0; i < BULK_STAGES; ++i) issue(i);
   }
 
@@ -438,9 +451,10 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
   for (long long i = 0;; ++i) {
     const long long t = blockIdx.x + i * gridDim.x;
     if (t >= ntiles) break;
+    if (t * BULK_TILE + q * BULK_QPX >= HW) break;              // this quarter of the last tile is past the end: no load was issued
     const unsigned tc_next = tc_load(t + gridDim.x);
     const int s = static_cast<int>(i % BULK_STAGES);
-    lin_wait(lin_smem_u32(&bars[s]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
+    lin_wait(lin_smem_u32(&bars[s * BULK_NQ + q]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
     const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * 4;
     const long long pix = t * BULK_TILE + tid * 4;
     const bool live = pix < HW;                                  // HW % 4 == 0: a thread's 4 pixels are all in or all out
@@ -462,12 +476,12 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
 #pragma unroll
       for (int c = 0; c < CT; ++c) { b[c][0] = zero2; b[c][1] = zero2; }
     }
-    // operands are in registers: hand the stage back; the last warp to do so refills it with tile i + STAGES
+    // operands are in registers: hand the slice back; the last warp of the quarter refills it with tile i + STAGES
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
-      if (atomicAdd(&done[s], 1u) == NW - 1) {
-        done[s] = 0u;
+      if (atomicAdd(&done[s * BULK_NQ + q], 1u) == BULK_QWARPS - 1) {
+        done[s * BULK_NQ + q] = 0u;
         issue(i + BULK_STAGES);
       }
     }
@@ -492,20 +506,46 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
 
+// FUVS_LINEAR_NQ = 1 | 4 slice pipelines per CTA, FUVS_LINEAR_PDL = 0 | 1 (A/B switches; defaults from measurements)
+static int linear_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
+}
+
+template <int CT, bool COUNTS, bool LOGITS, int NQ>
+static int launch_bulk_nq(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
+                          const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
+                          cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + BULK_STAGES * BULK_NQ_MAX * 12 + 32;
+  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS, NQ>;
+  static SmemOptIn optin;
+  if (!optin.ensure(kern, static_cast<int>(smem))) return 1;   // caller uses the register-load kernel
+  static const int pdl = linear_env("FUVS_LINEAR_PDL", 1);
+  const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
+  const long long cap = sm_count();
+  const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(BULK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, prev, next, HW, n, labels, logits, tc_prev, reinterpret_cast<unsigned long long*>(counts),
+                     ignore_index, w, 1.0f, pdl);
+  return check_launch("fuvs_linear_blend_argmax(bulk)");
+}
+
 template <int CT, bool COUNTS, bool LOGITS>
 static int launch_bulk(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                        const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                        cudaStream_t st) {
-  const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + 64;
-  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS>;
-  static SmemOptIn optin;
-  if (!optin.ensure(kern, static_cast<int>(smem))) return 1;   // caller uses the register-load kernel
-  const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
-  const long long cap = sm_count();
-  const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
-  kern<<<grid, BULK_THREADS, smem, st>>>(prev, next, HW, n, labels, logits, tc_prev,
-                                         reinterpret_cast<unsigned long long*>(counts), ignore_index, w, 1.0f);
-  return check_launch("fuvs_linear_blend_argmax(bulk)");
+  static const int nq = linear_env("FUVS_LINEAR_NQ", 1);
+  if (nq == 4) return launch_bulk_nq<CT, COUNTS, LOGITS, 4>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  return launch_bulk_nq<CT, COUNTS, LOGITS, 1>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -9,6 +9,8 @@
 // Integer-only: per-thread packed 8-bit counters -> REDUX warp sums -> one
 // shared-memory merge per block -> 3K 64-bit atomics per block.  No float
 // atomics anywhere, so results are run-to-run identical.
+#include <cstdlib>
+
 #include "fuvs_common.cuh"
 
 namespace fuvs {
@@ -147,8 +149,8 @@ template <> struct Lab16<long long> {
   }
 };
 
-template <typename PT, typename TT, int KT>
-__global__ void __launch_bounds__(256)
+template <typename PT, typename TT, int KT, bool PIPE>
+__global__ void __launch_bounds__(256, PIPE ? 2 : 1)
 confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long long ngroups, long long ignore,
                      int mutate, unsigned long long* __restrict__ counts) {
   using FC = FieldCfg<KT>;
@@ -157,11 +159,29 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
   cnt.init();
   int since_spill = 0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+  long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // software pipeline: the loads of the next group are in flight while this one is counted (a thread's ~250
+  // instructions per group used to start only after its 9 loads had come back from DRAM)
+  Lab16<PT> o_nxt;
+  Lab16<TT> t_nxt;
+  if (PIPE && g < ngroups) {
+    o_nxt.load(pred + g * 16, mutate == 0);
+    t_nxt.load(target + g * 16, true);
+  }
+  for (; g < ngroups; g += stride) {
     Lab16<PT> o;
     Lab16<TT> t;
-    o.load(pred + g * 16, mutate == 0);
-    t.load(target + g * 16, true);
+    if (PIPE) {
+      o = o_nxt;
+      t = t_nxt;
+      if (g + stride < ngroups) {
+        o_nxt.load(pred + (g + stride) * 16, mutate == 0);
+        t_nxt.load(target + (g + stride) * 16, true);
+      }
+    } else {
+      o.load(pred + g * 16, mutate == 0);
+      t.load(target + g * 16, true);
+    }
     bool changed = false;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -192,11 +212,18 @@ static int launch_confusion_v16(void* pred, const void* target, long long ngroup
                                 long long* counts, cudaStream_t st) {
   auto cu = reinterpret_cast<unsigned long long*>(counts);
   const int threads = 256;
+  static const bool pipe = []() { const char* e = getenv("FUVS_CONF_PIPE"); return !(e && e[0] == '0'); }();
 #define FUVS_CF16(KT_)                                                                                         \
   {                                                                                                            \
-    const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_>, ngroups, threads);                     \
-    confusion_v16_kernel<PT, TT, KT_><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
-                                                               ngroups, ignore, mutate, cu);                   \
+    if (pipe) {                                                                                                \
+      const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, true>, ngroups, threads);             \
+      confusion_v16_kernel<PT, TT, KT_, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
+                                                                       ngroups, ignore, mutate, cu);           \
+    } else {                                                                                                   \
+      const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, false>, ngroups, threads);            \
+      confusion_v16_kernel<PT, TT, KT_, false><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
+                                                                        ngroups, ignore, mutate, cu);          \
+    }                                                                                                          \
   }
   switch (K) {
     case 2: FUVS_CF16(2) break;
@@ -253,6 +280,41 @@ temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, 
 
 // Fast path of the temporal-consistency counts: K <= 5, ignore outside [0,K), HW % 16 == 0.  16 pixels per thread
 // (one 128-bit load per frame), field-packed counters (FieldCounts), one REDUX pass per warp at the end.
+// Per label the first version spent ~14 ALU instructions (two byte extractions, range checks and a select for each of
+// output and target, three adds, a compare and a select): 15 us for 5 x 1080p, ALU-bound at 0.8 TB/s.  Now a frame whose
+// 16 labels are all < KT (always, for arg-max output) gets its counter fields from one multiply per word (label bytes
+// times the field width are the shift amounts) and one or two shifts per label; the T term of a pair is the field sum
+// of the previous frame (one add per 16 labels), and the I term is a predicated add on the bytes of cur ^ last.
+// Frames with out-of-range labels (a caller's own label maps, ignore_index) take the per-label path.
+template <int KT>
+__device__ __forceinline__ unsigned tc_invalid(const uint4& w) {
+  constexpr unsigned ADD = (0x80u - KT) * 0x01010101u;
+  const unsigned a = (((w.x & 0x7f7f7f7fu) + ADD) | w.x), b = (((w.y & 0x7f7f7f7fu) + ADD) | w.y);
+  const unsigned c = (((w.z & 0x7f7f7f7fu) + ADD) | w.z), d = (((w.w & 0x7f7f7f7fu) + ADD) | w.w);
+  return (a | b | c | d) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned tc_one_shl_wrap(unsigned c) {
+  unsigned d;
+  asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(c));
+  return d;
+}
+template <int KT>
+__device__ __forceinline__ unsigned tc_fields(const uint4& w, unsigned (&fld)[16]) {
+  constexpr unsigned FW = FieldCfg<KT>::FW;
+  const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+  unsigned s = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned m = ws[j] * FW;             // bytes: FW * label <= 24, the low five bits of each are the shift
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      fld[4 * j + i] = tc_one_shl_wrap(m >> (8 * i));
+      s += fld[4 * j + i];
+    }
+  }
+  return s;
+}
+
 template <int KT>
 __global__ void __launch_bounds__(256)
 temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
@@ -271,9 +333,13 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
     const long long pix = v << 4;
     uint4 last = make_uint4(0u, 0u, 0u, 0u);
     bool have_last = false;
+    unsigned bad_last = 0u, s_last = 0u;
     if (tc_prev) {
       last = __ldg(reinterpret_cast<const uint4*>(tc_prev + pix));
       have_last = true;
+      bad_last = tc_invalid<KT>(last);
+      unsigned f[16];
+      s_last = tc_fields<KT>(last, f);          // only used when bad_last == 0
     }
     int since_spill = 0;
     uint4 nxt = __ldcs(reinterpret_cast<const uint4*>(labels + pix));
@@ -281,17 +347,31 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
       const uint4 cur = nxt;
       if (p + 1 < n)   // software pipelining: the next frame's load is in flight while this one is counted
         nxt = __ldcs(reinterpret_cast<const uint4*>(labels + static_cast<long long>(p + 1) * HW + pix));
+      const unsigned bad_cur = tc_invalid<KT>(cur);
+      unsigned fld[16];
+      const unsigned s_cur = tc_fields<KT>(cur, fld);
       if (have_last) {
         const unsigned cw[4] = {cur.x, cur.y, cur.z, cur.w};
         const unsigned lw[4] = {last.x, last.y, last.z, last.w};
+        if ((bad_cur | bad_last) == 0u) {
+          cnt.accO += s_cur;
+          cnt.accT += s_last;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+          for (int w = 0; w < 4; ++w) {
+            const unsigned x = cw[w] ^ lw[w];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int o = (cw[w] >> (8 * i)) & 255u, t = (lw[w] >> (8 * i)) & 255u;
-            const unsigned ft = (t < KT) ? FieldCounts<KT>::field(t) : 0u;
-            const unsigned fo = (o < KT && t != ignore) ? FieldCounts<KT>::field(o) : 0u;
-            cnt.add(o, fo, t, ft);
+            for (int i = 0; i < 4; ++i) cnt.accI += ((x & (0xffu << (8 * i))) == 0u) ? fld[4 * w + i] : 0u;
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int o = (cw[w] >> (8 * i)) & 255u, t = (lw[w] >> (8 * i)) & 255u;
+              const unsigned ft = (t < KT) ? FieldCounts<KT>::field(t) : 0u;
+              const unsigned fo = (o < KT && t != ignore) ? FieldCounts<KT>::field(o) : 0u;
+              cnt.add(o, fo, t, ft);
+            }
           }
         }
         if (++since_spill >= FC::CAP / 16) {
@@ -300,6 +380,8 @@ temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long 
         }
       }
       last = cur;
+      bad_last = bad_cur;
+      s_last = s_cur;
       have_last = true;
     }
     cnt.spill();
