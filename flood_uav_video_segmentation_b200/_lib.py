@@ -14,7 +14,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfuvs.so")
+LIB_PATH = os.environ.get("FUVS_LIB_PATH") or os.path.join(_HERE, "lib", "libfuvs.so")   # override: developer A/B builds (build.py)
 
 FUVS_ABI_VERSION = 1
 FUVS_BINS_HISTC = 0

@@ -24,6 +24,12 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v",
 ]
+# developer A/B builds: FUVS_BUILD_TAG=x FUVS_BUILD_DEFINES="-DFOO -DBAR" writes lib/libfuvs_x.so (objects in build_x/);
+# FUVS_LIB_PATH selects which library _lib.py loads.  The shipped library is always the untagged default build.
+_TAG = os.environ.get("FUVS_BUILD_TAG", "")
+if _TAG:
+    LIB = os.path.join(LIBDIR, f"libfuvs_{_TAG}.so")
+    NVCC_FLAGS += os.environ.get("FUVS_BUILD_DEFINES", "").split()
 if os.environ.get("FUVS_STRIP_PROF"):   # developer instrumentation of dense_strip.cu (never set for the shipped build)
     NVCC_FLAGS.append("-DFUVS_STRIP_PROF")
 
@@ -45,7 +51,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + (f"_{_TAG}" if _TAG else ""))
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "fuvs.h"))
