@@ -379,8 +379,8 @@ __device__ __forceinline__ void lin_wait(uint32_t bar, uint32_t parity) {
 // NQ = 4 lets a quarter start when its own 20 KB have landed and refill as soon as its four warps hold their operands,
 // but its 2 KB bulk copies cost more than the decoupling gains: 24.0 vs 22.5 us per interval (FUVS_LINEAR_NQ=4 keeps
 // the variant reachable for re-measurement).
-template <int CT, bool COUNTS, bool LOGITS, int BULK_NQ>
-__global__ void __launch_bounds__(BULK_THREADS, 1)
+template <int CT, bool COUNTS, bool LOGITS, int BULK_NQ, int NP>
+__global__ void __launch_bounds__(BULK_TILE / (2 * NP), 1)
 linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __restrict__ next,
                                 long long HW, int n,
                                 uint8_t* __restrict__ labels, float* __restrict__ logits,
@@ -389,14 +389,16 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
                                 const BlendWeights wts, float one, int pdl) {
   extern __shared__ __align__(128) unsigned char lin_smem[];
   __shared__ unsigned sh[24];
+  constexpr int NPX = 2 * NP;                              // pixels per thread: 4 (512 threads) or 2 (1024 threads)
+  constexpr int THREADS = BULK_TILE / NPX;
   constexpr int BULK_QPX = BULK_TILE / BULK_NQ;
-  constexpr int BULK_QWARPS = BULK_THREADS / 32 / BULK_NQ;
+  constexpr int BULK_QWARPS = THREADS / 32 / BULK_NQ;
   const int nplanes = (n > 1) ? 2 * CT : CT;
   float* stage_base = reinterpret_cast<float*>(lin_smem);                               // [STAGES][2*CT][BULK_TILE]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(lin_smem + static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4);
   unsigned* done = reinterpret_cast<unsigned*>(bars + BULK_STAGES * BULK_NQ);           // [STAGES][NQ]
   const int tid = threadIdx.x, lane = tid & 31;
-  const int q = tid / (BULK_QPX / 4);                                                   // this thread's quarter
+  const int q = tid / (BULK_QPX / NPX);                                                   // this thread's quarter
   const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
   const u64 one2 = pack2(one, one);
   const float zero = __fsub_rn(one, one);
@@ -433,7 +435,7 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
                    ::"r"(lin_smem_u32(sb + static_cast<size_t>(p) * BULK_TILE)), "l"(g), "r"(bytes), "r"(bar) : "memory");
     }
   };
-  if ((tid & (BULK_QPX / 4 - 1)) == 0) {
+  if ((tid & (BULK_QPX / NPX - 1)) == 0) {
     for (int i = 0; i < BULK_STAGES; ++i) issue(i);
   }
 
@@ -444,8 +446,8 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
   // (long-scoreboard 2.2 warps per issue, profiles/r01_ncu_linear_final.txt)
   const bool have_tc = COUNTS && tc_prev != nullptr;
   auto tc_load = [&](long long tile) -> unsigned {
-    const long long px = tile * BULK_TILE + tid * 4;
-    return (have_tc && px < HW) ? __ldg(reinterpret_cast<const unsigned*>(tc_prev + px)) : 0u;
+    const long long px = tile * BULK_TILE + tid * NPX;
+    return (have_tc && px < HW) ? PixIO<NP>::load_labels(tc_prev + px) : 0u;
   };
   unsigned tc_word = tc_load(blockIdx.x);
   for (long long i = 0;; ++i) {
@@ -455,26 +457,31 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
     const unsigned tc_next = tc_load(t + gridDim.x);
     const int s = static_cast<int>(i % BULK_STAGES);
     lin_wait(lin_smem_u32(&bars[s * BULK_NQ + q]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
-    const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * 4;
-    const long long pix = t * BULK_TILE + tid * 4;
+    const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * NPX;
+    const long long pix = t * BULK_TILE + tid * NPX;
     const bool live = pix < HW;                                  // HW % 4 == 0: a thread's 4 pixels are all in or all out
-    u64 a[CT][2], b[CT][2];
+    u64 a[CT][NP], b[CT][NP];
+    auto lds = [&](const float* p, u64 (&d)[NP]) {
+      if constexpr (NP == 2) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        d[0] = pack2(v.x, v.y);
+        d[1] = pack2(v.z, v.w);
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        d[0] = pack2(v.x, v.y);
+      }
+    };
 #pragma unroll
-    for (int c = 0; c < CT; ++c) {
-      const float4 v = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(c) * BULK_TILE);
-      a[c][0] = pack2(v.x, v.y);
-      a[c][1] = pack2(v.z, v.w);
-    }
+    for (int c = 0; c < CT; ++c) lds(sb + static_cast<size_t>(c) * BULK_TILE, a[c]);
     if (n > 1) {
 #pragma unroll
-      for (int c = 0; c < CT; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(sb + static_cast<size_t>(CT + c) * BULK_TILE);
-        b[c][0] = pack2(v.x, v.y);
-        b[c][1] = pack2(v.z, v.w);
-      }
+      for (int c = 0; c < CT; ++c) lds(sb + static_cast<size_t>(CT + c) * BULK_TILE, b[c]);
     } else {
 #pragma unroll
-      for (int c = 0; c < CT; ++c) { b[c][0] = zero2; b[c][1] = zero2; }
+      for (int c = 0; c < CT; ++c) {
+#pragma unroll
+        for (int h = 0; h < NP; ++h) b[c][h] = zero2;
+      }
     }
     // operands are in registers: hand the slice back; the last warp of the quarter refills it with tile i + STAGES
     __syncwarp();
@@ -489,17 +496,18 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
       u64 probe = zero2;
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        probe = fma2_rn(a[c][0], zero2, probe);
-        probe = fma2_rn(a[c][1], zero2, probe);
-        probe = fma2_rn(b[c][0], zero2, probe);
-        probe = fma2_rn(b[c][1], zero2, probe);
+#pragma unroll
+        for (int h = 0; h < NP; ++h) {
+          probe = fma2_rn(a[c][h], zero2, probe);
+          probe = fma2_rn(b[c][h], zero2, probe);
+        }
       }
       float pr0, pr1;
       unpack2(probe, pr0, pr1);
       if ((pr0 == pr0) && (pr1 == pr1))
-        linear_frames<CT, 2, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
+        linear_frames<CT, NP, COUNTS, false, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
       else
-        linear_frames<CT, 2, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
+        linear_frames<CT, NP, COUNTS, true, LOGITS>(a, b, HW, pix, n, labels, logits, have_tc, tc_word, ignore_index, wts, one2, cnt);
     }
     tc_word = tc_next;
   }
@@ -512,12 +520,12 @@ static int linear_env(const char* name, int dflt) {
   return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
 }
 
-template <int CT, bool COUNTS, bool LOGITS, int NQ>
+template <int CT, bool COUNTS, bool LOGITS, int NQ, int NP>
 static int launch_bulk_nq(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                           const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                           cudaStream_t st) {
   const size_t smem = static_cast<size_t>(BULK_STAGES) * 2 * CT * BULK_TILE * 4 + BULK_STAGES * BULK_NQ_MAX * 12 + 32;
-  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS, NQ>;
+  auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS, NQ, NP>;
   static SmemOptIn optin;
   if (!optin.ensure(kern, static_cast<int>(smem))) return 1;   // caller uses the register-load kernel
   static const int pdl = linear_env("FUVS_LINEAR_PDL", 1);
@@ -526,7 +534,7 @@ static int launch_bulk_nq(const float* prev, const float* next, long long HW, in
   const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(BULK_THREADS);
+  cfg.blockDim = dim3(BULK_TILE / (2 * NP));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -544,8 +552,10 @@ static int launch_bulk(const float* prev, const float* next, long long HW, int n
                        const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                        cudaStream_t st) {
   static const int nq = linear_env("FUVS_LINEAR_NQ", 1);
-  if (nq == 4) return launch_bulk_nq<CT, COUNTS, LOGITS, 4>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-  return launch_bulk_nq<CT, COUNTS, LOGITS, 1>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  static const int px = linear_env("FUVS_LINEAR_BULK_PX", 4);       // 4 pixels x 512 threads | 2 pixels x 1024 threads
+  if (nq == 4) return launch_bulk_nq<CT, COUNTS, LOGITS, 4, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  if (px == 2) return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 1>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -362,6 +362,35 @@ def test_temporal_counts(cuda, K, H, W):
         assert np.array_equal(got.cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("n", [16, 29, 30, 31, 45, 60])
+def test_counter_fields_saturate(cuda, n):
+    """Every pixel of every frame has the same label, so one 6-bit counter field (C = 5) takes all the load: the
+    spill schedule of the field-packed counters (linear, block-rows and temporal-counts kernels) must keep it below 64
+    between spills for any interval length, including the two extra pairs the block kernel counts after its frame loop."""
+    C, H, W = 5, 64, 96
+    g = torch.Generator().manual_seed(n)
+    o, o_next = torch.randn(1, C, H, W, generator=g), torch.randn(1, C, H, W, generator=g)
+    o[:, 2] += 30.0
+    o_next[:, 2] += 30.0
+    tc_prev = torch.full((H, W), 2, dtype=torch.uint8)
+    gl = flow_grids(H, W, n, "block", clip=3, side=0)
+    gr = flow_grids(H, W, n, "block", clip=3, side=1)
+    for no_warp in (True, False):
+        _, ref_labels = oracle_interval(o, o_next, gl, gr, n, no_warp, cuda)
+        assert bool((ref_labels == 2).all())
+        ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+        counts = kernels.new_counts(C, cuda)
+        if no_warp:
+            labels, _ = kernels.linear_blend_argmax(o[0].to(cuda), o_next[0].to(cuda), n, tc_prev=tc_prev.to(cuda), counts=counts)
+        else:
+            labels, _ = kernels.block_interval(o.to(cuda), o_next.to(cuda), [x.to(cuda) for x in gl], [x.to(cuda) for x in gr],
+                                               n, want_labels=True, tc_prev=tc_prev.to(cuda), counts=counts)
+        assert torch.equal(labels.long(), ref_labels)
+        assert np.array_equal(counts.cpu().numpy(), ref_counts), f"no_warp={no_warp}"
+        got = kernels.temporal_counts(labels, C, 255, tc_prev=tc_prev.to(cuda))
+        assert np.array_equal(got.cpu().numpy(), ref_counts)
+
+
 def test_errors_are_loud(cuda):
     with pytest.raises(kernels.FuvsError):
         kernels.linear_blend_argmax(torch.zeros(5, 8, 8), torch.zeros(5, 8, 8), 5)          # CPU tensors
