@@ -118,6 +118,96 @@ static int persistent_grid(K kernel, long long work_items, int threads) {
 // per iteration with 128-bit loads, counts in three 32-bit registers with 6/8-bit class fields (FieldCounts) and the
 // warp reduction happens once per kernel.
 // ---------------------------------------------------------------------------
+template <int KT>
+__device__ __forceinline__ unsigned tc_invalid(const uint4& w) {
+  constexpr unsigned ADD = (0x80u - KT) * 0x01010101u;
+  const unsigned a = (((w.x & 0x7f7f7f7fu) + ADD) | w.x), b = (((w.y & 0x7f7f7f7fu) + ADD) | w.y);
+  const unsigned c = (((w.z & 0x7f7f7f7fu) + ADD) | w.z), d = (((w.w & 0x7f7f7f7fu) + ADD) | w.w);
+  return (a | b | c | d) & 0x80808080u;
+}
+__device__ __forceinline__ unsigned tc_one_shl_wrap(unsigned c) {
+  unsigned d;
+  asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(c));
+  return d;
+}
+template <int KT>
+__device__ __forceinline__ unsigned tc_fields(const uint4& w, unsigned (&fld)[16]) {
+  constexpr unsigned FW = FieldCfg<KT>::FW;
+  const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+  unsigned s = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned m = ws[j] * FW;             // bytes: FW * label <= 24, the low five bits of each are the shift
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      fld[4 * j + i] = tc_one_shl_wrap(m >> (8 * i));
+      s += fld[4 * j + i];
+    }
+  }
+  return s;
+}
+
+
+// ---------------------------------------------------------------------------
+// Byte-domain counting of one group of 16 (prediction, target) labels for fuvs_confusion's fast path.  The per-label
+// code below it works on 64-bit values (range checks, ignore test and three field updates: ~20 ALU instructions per
+// label for int64 targets, which made the kernel ALU-bound at 0.63 of the HBM roofline).  Here int64 labels are first
+// narrowed to bytes (group-wide OR of the high words and one PRMT per two labels); a group whose predictions are all
+// < KT and whose targets are all < KT or == ignore_index then gets its counter fields from one multiply per word like
+// fuvs_temporal_counts.  Returns false when the group needs the per-label path (out-of-range labels, an
+// ignore_index that does not fit a byte).  igff: 0xff in the bytes whose target is ignore_index.
+// ---------------------------------------------------------------------------
+template <int KT>
+__device__ __forceinline__ bool confusion_bytes16(const unsigned (&pw)[4], const unsigned (&tw)[4], bool ig_valid,
+                                                  unsigned ig4, bool refuse_ignored, FieldCounts<KT>& cnt,
+                                                  unsigned (&igff)[4], bool& any_ignored) {
+  constexpr unsigned ADD = (0x80u - KT) * 0x01010101u;
+  unsigned pbad = 0u, tbad = 0u, anyig = 0u;
+  unsigned ig80[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pbad |= ((pw[j] & 0x7f7f7f7fu) + ADD) | pw[j];
+    const unsigned tb = ((tw[j] & 0x7f7f7f7fu) + ADD) | tw[j];
+    const unsigned x = tw[j] ^ ig4;
+    const unsigned nz = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;          // bit 7 of a byte set iff the byte of x is non-zero
+    ig80[j] = ig_valid ? (~nz & 0x80808080u) : 0u;
+    tbad |= tb & ~ig80[j];
+    anyig |= ig80[j];
+  }
+  if (((pbad | tbad) & 0x80808080u) != 0u) return false;
+  any_ignored = anyig != 0u;
+  if (refuse_ignored && any_ignored) return false;
+  uint4 pq = make_uint4(pw[0], pw[1], pw[2], pw[3]), tq;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) igff[j] = (ig80[j] >> 7) * 0xffu;
+  tq = make_uint4(tw[0] & ~igff[0], tw[1] & ~igff[1], tw[2] & ~igff[2], tw[3] & ~igff[3]);   // ignored bytes -> 0 (masked below)
+  unsigned fo[16], ft[16];
+  const unsigned s_o = tc_fields<KT>(pq, fo);
+  const unsigned s_t = tc_fields<KT>(tq, ft);
+  if (!any_ignored) {
+    cnt.accO += s_o;
+    cnt.accT += s_t;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool keep = (ig80[j] & (0x80u << (8 * i))) == 0u;       // output[target == ignore] = ignore: nothing counts
+        cnt.accO += keep ? fo[4 * j + i] : 0u;
+        cnt.accT += keep ? ft[4 * j + i] : 0u;
+      }
+    }
+  }
+  // a prediction (< KT) never equals an ignored target byte (ignore_index is outside the classes): no mask needed
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned x = pw[j] ^ tw[j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cnt.accI += ((x & (0xffu << (8 * i))) == 0u) ? fo[4 * j + i] : 0u;
+  }
+  return true;
+}
+
 template <typename T> struct Lab16;
 template <> struct Lab16<uint8_t> {
   uint4 w;
@@ -133,6 +223,14 @@ template <> struct Lab16<uint8_t> {
     word = (word & ~(255u << (8 * (i & 3)))) | ((static_cast<unsigned>(v) & 255u) << (8 * (i & 3)));
   }
   __device__ __forceinline__ void store(uint8_t* p) const { *reinterpret_cast<uint4*>(p) = w; }
+  __device__ __forceinline__ bool narrow(unsigned (&b)[4]) const { b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w; return true; }
+  // byte-wise: bytes flagged in ff take the bytes of v4
+  __device__ __forceinline__ void merge_bytes(const unsigned (&ff)[4], unsigned v4) {
+    w.x = (w.x & ~ff[0]) | (v4 & ff[0]); w.y = (w.y & ~ff[1]) | (v4 & ff[1]);
+    w.z = (w.z & ~ff[2]) | (v4 & ff[2]); w.w = (w.w & ~ff[3]) | (v4 & ff[3]);
+  }
+  __device__ __forceinline__ void from_bytes(const unsigned (&b)[4]) { w = make_uint4(b[0], b[1], b[2], b[3]); }
+  static constexpr bool kByteMerge = true;
 };
 template <> struct Lab16<long long> {
   longlong2 w[8];
@@ -147,6 +245,22 @@ template <> struct Lab16<long long> {
 #pragma unroll
     for (int k = 0; k < 8; ++k) reinterpret_cast<longlong2*>(p)[k] = w[k];
   }
+  // low bytes of the 16 values; false when a value does not fit a byte (negative, >= 256)
+  __device__ __forceinline__ bool narrow(unsigned (&b)[4]) const {
+    unsigned hi_or = 0u, lo_or = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned long long v0 = w[2 * j].x, v1 = w[2 * j].y, v2 = w[2 * j + 1].x, v3 = w[2 * j + 1].y;
+      const unsigned l0 = static_cast<unsigned>(v0), l1 = static_cast<unsigned>(v1), l2 = static_cast<unsigned>(v2), l3 = static_cast<unsigned>(v3);
+      hi_or |= static_cast<unsigned>(v0 >> 32) | static_cast<unsigned>(v1 >> 32) | static_cast<unsigned>(v2 >> 32) | static_cast<unsigned>(v3 >> 32);
+      lo_or |= l0 | l1 | l2 | l3;
+      b[j] = __byte_perm(__byte_perm(l0, l1, 0x0040), __byte_perm(l2, l3, 0x0040), 0x5410);
+    }
+    return hi_or == 0u && lo_or < 256u;
+  }
+  __device__ __forceinline__ void merge_bytes(const unsigned (&)[4], unsigned) {}
+  __device__ __forceinline__ void from_bytes(const unsigned (&)[4]) {}
+  static constexpr bool kByteMerge = false;
 };
 
 template <typename PT, typename TT, int KT, bool PIPE>
@@ -183,6 +297,36 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
       t.load(target + g * 16, true);
     }
     bool changed = false;
+    {
+      unsigned pw[4], tw[4], igff[4];
+      bool any_ignored = false;
+      const bool ig_valid = ignore >= 0 && ignore <= 255;
+      const unsigned ig4 = (static_cast<unsigned>(ignore) & 255u) * 0x01010101u;
+      // in-place substitution on int64 predictions stays on the per-label path (a rewrite of 128 bytes per group)
+      bool counted = false;
+      if (o.narrow(pw) & t.narrow(tw))
+        counted = confusion_bytes16<KT>(pw, tw, ig_valid, ig4, mutate && !Lab16<PT>::kByteMerge, cnt, igff, any_ignored);
+      if (counted) {
+        if (mutate && any_ignored) {
+          Lab16<PT> m;
+          m.from_bytes(pw);
+          m.merge_bytes(igff, ig4);
+          m.store(pred + g * 16);
+        }
+        since_spill += 16;
+        if (since_spill + 16 > FC::CAP) {
+          cnt.spill();
+          since_spill = 0;
+        }
+        continue;
+      }
+      // rare: out-of-range labels.  The 64-bit values are read again (L1/L2 hits) so that their 64 registers are not
+      // held across the byte path above — that cost two thirds of the occupancy.
+      if (!PIPE) {
+        o.load(pred + g * 16, false);
+        t.load(target + g * 16, false);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const long long tv = t.get(i);
@@ -212,17 +356,23 @@ static int launch_confusion_v16(void* pred, const void* target, long long ngroup
                                 long long* counts, cudaStream_t st) {
   auto cu = reinterpret_cast<unsigned long long*>(counts);
   const int threads = 256;
+  // software pipelining only for byte labels: with int64 operands two groups in flight do not fit the registers
   static const bool pipe = []() { const char* e = getenv("FUVS_CONF_PIPE"); return !(e && e[0] == '0'); }();
 #define FUVS_CF16(KT_)                                                                                         \
   {                                                                                                            \
-    if (pipe) {                                                                                                \
-      const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, true>, ngroups, threads);             \
-      confusion_v16_kernel<PT, TT, KT_, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
-                                                                       ngroups, ignore, mutate, cu);           \
-    } else {                                                                                                   \
+    bool launched = false;                                                                                     \
+    if constexpr (sizeof(PT) == 1 && sizeof(TT) == 1) {                                                        \
+      if (pipe) {                                                                                              \
+        const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, true>, ngroups, threads);           \
+        confusion_v16_kernel<PT, TT, KT_, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),              \
+                                                                         static_cast<const TT*>(target), ngroups, ignore, mutate, cu); \
+        launched = true;                                                                                       \
+      }                                                                                                        \
+    }                                                                                                          \
+    if (!launched) {                                                                                           \
       const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, false>, ngroups, threads);            \
-      confusion_v16_kernel<PT, TT, KT_, false><<<grid, threads, 0, st>>>(static_cast<PT*>(pred), static_cast<const TT*>(target), \
-                                                                        ngroups, ignore, mutate, cu);          \
+      confusion_v16_kernel<PT, TT, KT_, false><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),               \
+                                                                        static_cast<const TT*>(target), ngroups, ignore, mutate, cu); \
     }                                                                                                          \
   }
   switch (K) {
@@ -286,35 +436,6 @@ temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, 
 // times the field width are the shift amounts) and one or two shifts per label; the T term of a pair is the field sum
 // of the previous frame (one add per 16 labels), and the I term is a predicated add on the bytes of cur ^ last.
 // Frames with out-of-range labels (a caller's own label maps, ignore_index) take the per-label path.
-template <int KT>
-__device__ __forceinline__ unsigned tc_invalid(const uint4& w) {
-  constexpr unsigned ADD = (0x80u - KT) * 0x01010101u;
-  const unsigned a = (((w.x & 0x7f7f7f7fu) + ADD) | w.x), b = (((w.y & 0x7f7f7f7fu) + ADD) | w.y);
-  const unsigned c = (((w.z & 0x7f7f7f7fu) + ADD) | w.z), d = (((w.w & 0x7f7f7f7fu) + ADD) | w.w);
-  return (a | b | c | d) & 0x80808080u;
-}
-__device__ __forceinline__ unsigned tc_one_shl_wrap(unsigned c) {
-  unsigned d;
-  asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(c));
-  return d;
-}
-template <int KT>
-__device__ __forceinline__ unsigned tc_fields(const uint4& w, unsigned (&fld)[16]) {
-  constexpr unsigned FW = FieldCfg<KT>::FW;
-  const unsigned ws[4] = {w.x, w.y, w.z, w.w};
-  unsigned s = 0u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const unsigned m = ws[j] * FW;             // bytes: FW * label <= 24, the low five bits of each are the shift
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      fld[4 * j + i] = tc_one_shl_wrap(m >> (8 * i));
-      s += fld[4 * j + i];
-    }
-  }
-  return s;
-}
-
 template <int KT>
 __global__ void __launch_bounds__(256)
 temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
