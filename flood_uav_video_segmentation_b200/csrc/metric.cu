@@ -223,6 +223,20 @@ template <> struct Lab16<uint8_t> {
     word = (word & ~(255u << (8 * (i & 3)))) | ((static_cast<unsigned>(v) & 255u) << (8 * (i & 3)));
   }
   __device__ __forceinline__ void store(uint8_t* p) const { *reinterpret_cast<uint4*>(p) = w; }
+  // interleaved mapping (see confusion_v16_kernel): label pair k of lane l sits at pair index 32 k + l of the warp's block
+  __device__ __forceinline__ void load_il(const uint8_t* blk, int lane, bool stream) {
+    const unsigned short* q = reinterpret_cast<const unsigned short*>(blk) + lane;
+    unsigned h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = stream ? __ldcs(q + 32 * k) : q[32 * k];
+    w = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+  }
+  __device__ __forceinline__ void store_il(uint8_t* blk, int lane) const {
+    unsigned short* q = reinterpret_cast<unsigned short*>(blk) + lane;
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[32 * k] = static_cast<unsigned short>(ws[k >> 1] >> (16 * (k & 1)));
+  }
   __device__ __forceinline__ bool narrow(unsigned (&b)[4]) const { b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w; return true; }
   // byte-wise: bytes flagged in ff take the bytes of v4
   __device__ __forceinline__ void merge_bytes(const unsigned (&ff)[4], unsigned v4) {
@@ -245,6 +259,16 @@ template <> struct Lab16<long long> {
 #pragma unroll
     for (int k = 0; k < 8; ++k) reinterpret_cast<longlong2*>(p)[k] = w[k];
   }
+  __device__ __forceinline__ void load_il(const long long* blk, int lane, bool stream) {
+    const longlong2* q = reinterpret_cast<const longlong2*>(blk) + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = stream ? __ldcs(q + 32 * k) : q[32 * k];
+  }
+  __device__ __forceinline__ void store_il(long long* blk, int lane) const {
+    longlong2* q = reinterpret_cast<longlong2*>(blk) + lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[32 * k] = w[k];
+  }
   // low bytes of the 16 values; false when a value does not fit a byte (negative, >= 256)
   __device__ __forceinline__ bool narrow(unsigned (&b)[4]) const {
     unsigned hi_or = 0u, lo_or = 0u;
@@ -263,7 +287,11 @@ template <> struct Lab16<long long> {
   static constexpr bool kByteMerge = false;
 };
 
-template <typename PT, typename TT, int KT, bool PIPE>
+// IL (an int64 operand): a thread's 16 labels are the pairs 32 k + lane (k = 0..7) of its warp's 512-label block, so
+// that every load instruction of the warp covers one contiguous 512-byte run.  With 128 contiguous bytes per thread
+// each 128-bit load touched 32 different lines (8 instructions per line): the L1 tag stage, not HBM, set the pace
+// (0.62 of the roofline whatever the ALU work).  Byte operands then come as eight 16-bit loads.
+template <typename PT, typename TT, int KT, bool PIPE, bool IL>
 __global__ void __launch_bounds__(256, PIPE ? 2 : 1)
 confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long long ngroups, long long ignore,
                      int mutate, unsigned long long* __restrict__ counts) {
@@ -272,29 +300,37 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
   FieldCounts<KT> cnt;
   cnt.init();
   int since_spill = 0;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  // unit of work: one 16-label group per thread, or (IL) one 512-label block per warp
+  const long long stride = IL ? static_cast<long long>(gridDim.x) * (blockDim.x >> 5) : static_cast<long long>(gridDim.x) * blockDim.x;
+  long long g = IL ? static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)
+                   : static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  auto ld = [&](long long gi, Lab16<PT>& oo, Lab16<TT>& tt, bool stream) {
+    if (IL) {
+      oo.load_il(pred + gi * 512, lane, stream && mutate == 0);
+      tt.load_il(target + gi * 512, lane, stream);
+    } else {
+      oo.load(pred + gi * 16, stream && mutate == 0);
+      tt.load(target + gi * 16, stream);
+    }
+  };
+  auto st = [&](long long gi, const Lab16<PT>& oo) {
+    if (IL) oo.store_il(pred + gi * 512, lane); else oo.store(pred + gi * 16);
+  };
   // software pipeline: the loads of the next group are in flight while this one is counted (a thread's ~250
   // instructions per group used to start only after its 9 loads had come back from DRAM)
   Lab16<PT> o_nxt;
   Lab16<TT> t_nxt;
-  if (PIPE && g < ngroups) {
-    o_nxt.load(pred + g * 16, mutate == 0);
-    t_nxt.load(target + g * 16, true);
-  }
+  if (PIPE && g < ngroups) ld(g, o_nxt, t_nxt, true);
   for (; g < ngroups; g += stride) {
     Lab16<PT> o;
     Lab16<TT> t;
     if (PIPE) {
       o = o_nxt;
       t = t_nxt;
-      if (g + stride < ngroups) {
-        o_nxt.load(pred + (g + stride) * 16, mutate == 0);
-        t_nxt.load(target + (g + stride) * 16, true);
-      }
+      if (g + stride < ngroups) ld(g + stride, o_nxt, t_nxt, true);
     } else {
-      o.load(pred + g * 16, mutate == 0);
-      t.load(target + g * 16, true);
+      ld(g, o, t, true);
     }
     bool changed = false;
     {
@@ -311,7 +347,7 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
           Lab16<PT> m;
           m.from_bytes(pw);
           m.merge_bytes(igff, ig4);
-          m.store(pred + g * 16);
+          st(g, m);
         }
         since_spill += 16;
         if (since_spill + 16 > FC::CAP) {
@@ -322,10 +358,7 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
       }
       // rare: out-of-range labels.  The 64-bit values are read again (L1/L2 hits) so that their 64 registers are not
       // held across the byte path above — that cost two thirds of the occupancy.
-      if (!PIPE) {
-        o.load(pred + g * 16, false);
-        t.load(target + g * 16, false);
-      }
+      if (!PIPE) ld(g, o, t, false);
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -341,7 +374,7 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
       cnt.accT += ft;
       cnt.accI += (ov == tv) ? fo : 0u;
     }
-    if (mutate && changed) o.store(pred + g * 16);
+    if (mutate && changed) st(g, o);
     since_spill += 16;
     if (since_spill + 16 > FC::CAP) {
       cnt.spill();
@@ -352,27 +385,35 @@ confusion_v16_kernel(PT* __restrict__ pred, const TT* __restrict__ target, long 
 }
 
 template <typename PT, typename TT>
-static int launch_confusion_v16(void* pred, const void* target, long long ngroups, int K, long long ignore, int mutate,
+static constexpr bool conf_interleaved() { return sizeof(PT) == 8 || sizeof(TT) == 8; }
+// labels one work unit of the fast path covers (a thread's group, or a warp's block with int64 operands)
+template <typename PT, typename TT>
+static constexpr int conf_unit() { return conf_interleaved<PT, TT>() ? 512 : 16; }
+
+template <typename PT, typename TT>
+static int launch_confusion_v16(void* pred, const void* target, long long nunits, int K, long long ignore, int mutate,
                                 long long* counts, cudaStream_t st) {
   auto cu = reinterpret_cast<unsigned long long*>(counts);
   const int threads = 256;
+  constexpr bool IL = conf_interleaved<PT, TT>();
+  const long long work_threads = IL ? nunits * 32 : nunits;
   // software pipelining only for byte labels: with int64 operands two groups in flight do not fit the registers
   static const bool pipe = []() { const char* e = getenv("FUVS_CONF_PIPE"); return !(e && e[0] == '0'); }();
 #define FUVS_CF16(KT_)                                                                                         \
   {                                                                                                            \
     bool launched = false;                                                                                     \
-    if constexpr (sizeof(PT) == 1 && sizeof(TT) == 1) {                                                        \
+    if constexpr (!IL) {                                                                                       \
       if (pipe) {                                                                                              \
-        const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, true>, ngroups, threads);           \
-        confusion_v16_kernel<PT, TT, KT_, true><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),              \
-                                                                         static_cast<const TT*>(target), ngroups, ignore, mutate, cu); \
+        const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, true, IL>, work_threads, threads);  \
+        confusion_v16_kernel<PT, TT, KT_, true, IL><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),          \
+                                                                             static_cast<const TT*>(target), nunits, ignore, mutate, cu); \
         launched = true;                                                                                       \
       }                                                                                                        \
     }                                                                                                          \
     if (!launched) {                                                                                           \
-      const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, false>, ngroups, threads);            \
-      confusion_v16_kernel<PT, TT, KT_, false><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),               \
-                                                                        static_cast<const TT*>(target), ngroups, ignore, mutate, cu); \
+      const int grid = persistent_grid(confusion_v16_kernel<PT, TT, KT_, false, IL>, work_threads, threads);   \
+      confusion_v16_kernel<PT, TT, KT_, false, IL><<<grid, threads, 0, st>>>(static_cast<PT*>(pred),           \
+                                                                            static_cast<const TT*>(target), nunits, ignore, mutate, cu); \
     }                                                                                                          \
   }
   switch (K) {
@@ -567,10 +608,11 @@ static int launch_confusion(void* pred, const void* target, long long N, int K, 
   const int threads = 256;
   // fast path: histc binning, 2 <= K <= 5, ignore outside the classes, 16-byte aligned label arrays; the
   // N % 16 tail goes through the general kernel below
-  if (!np_bins && K >= 2 && K <= 5 && (ignore < 0 || ignore >= K) && N >= 16 && aligned16(pred) && aligned16(target)) {
-    const long long ngroups = N / 16;
-    if (int e = launch_confusion_v16<PT, TT>(pred, target, ngroups, K, ignore, mutate, counts, st)) return e;
-    const long long done = ngroups * 16;
+  constexpr int UNIT = conf_unit<PT, TT>();
+  if (!np_bins && K >= 2 && K <= 5 && (ignore < 0 || ignore >= K) && N >= UNIT && aligned16(pred) && aligned16(target)) {
+    const long long nunits = N / UNIT;
+    if (int e = launch_confusion_v16<PT, TT>(pred, target, nunits, K, ignore, mutate, counts, st)) return e;
+    const long long done = nunits * UNIT;
     if (done == N) return FUVS_OK;
     pred = static_cast<PT*>(pred) + done;
     target = static_cast<const TT*>(target) + done;
