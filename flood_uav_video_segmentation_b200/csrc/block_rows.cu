@@ -13,6 +13,8 @@
 //            memory, does the vertical two-terms (2 instructions per value), blends with packed FP32x2, arg-maxes and
 //            counts exactly like linear.cu.
 // Same ATen arithmetic as block.cu (up_coord / two_term policies), so results are bit-identical.
+#include <cstdlib>
+
 #include "fuvs_common.cuh"
 #include "pix4.cuh"
 
@@ -254,6 +256,8 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
   // never diverge on the row loop; as wide as the budget allows up to 256 (4 rows in flight per CTA)
   int XW = 256;
   while (XW > 128 && per_col * XW > budget) XW -= 128;
+  static const int xw_env = []() { const char* e = getenv("FUVS_BLOCK_XW"); return e ? atoi(e) : 0; }();   // A/B switch
+  if (xw_env >= 16 && xw_env <= 1024 && (xw_env & 3) == 0 && BR_THREADS % (xw_env / 4) == 0) XW = xw_env;
   if (per_col * XW > budget) return 1;
   if (W < XW) XW = (W + 3) & ~3;
   const int nchunks = (W + XW - 1) / XW;
