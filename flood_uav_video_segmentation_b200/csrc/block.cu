@@ -44,6 +44,35 @@ upsample_bilinear_ac_kernel(const float* __restrict__ src, float* __restrict__ d
   }
 }
 
+// Wout % 4 == 0 and a 16-byte aligned destination: 4 consecutive pixels per thread (one row coordinate, one 128-bit
+// store), all planes of a pixel group in one thread so the coordinate arithmetic is paid once.  Same up_fetch<>
+// arithmetic as above.  (The key frames of the dense / block routes come through here: 41 MB per 1080p key frame.)
+template <class NM>
+__global__ void __launch_bounds__(256)
+upsample_bilinear_ac_v4_kernel(const float* __restrict__ src, float* __restrict__ dst, long long planes, int Hin,
+                               int Win, int Hout, int Wout, float sh, float sw) {
+  const int groups = Wout >> 2;
+  const long long items = static_cast<long long>(Hout) * groups;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= items) return;
+  const int y = static_cast<int>(t / groups), x = static_cast<int>(t - static_cast<long long>(y) * groups) << 2;
+  const UpCoord hc = up_coord<NM>(sh, y, Hin);
+  UpCoord wc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wc[i] = up_coord<NM>(sw, x + i, Win);
+  const long long in_plane = static_cast<long long>(Hin) * Win, out_plane = static_cast<long long>(Hout) * Wout;
+  float* o = dst + static_cast<long long>(y) * Wout + x;
+  for (long long pl = blockIdx.y; pl < planes; pl += gridDim.y) {
+    const float* sp = src + pl * in_plane;
+    float4 v;
+    v.x = up_fetch<NM>(sp, Win, hc, wc[0]);
+    v.y = up_fetch<NM>(sp, Win, hc, wc[1]);
+    v.z = up_fetch<NM>(sp, Win, hc, wc[2]);
+    v.w = up_fetch<NM>(sp, Win, hc, wc[3]);
+    *reinterpret_cast<float4*>(o + pl * out_plane) = v;
+  }
+}
+
 static inline float ac_scale(int in_size, int out_size) {
   // area_pixel_compute_scale<float>(in, out, align_corners=true): UpSample.cuh
   return out_size > 1 ? static_cast<float>(in_size - 1) / (out_size - 1) : 0.f;
@@ -54,6 +83,19 @@ static int launch_upsample(const float* src, float* dst, long long planes, int H
                            cudaStream_t st) {
   const long long out_plane = static_cast<long long>(Hout) * Wout;
   const int threads = 256;
+  static const bool v4 = []() { const char* e = getenv("FUVS_UPSAMPLE_V4"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (v4 && (Wout & 3) == 0 && aligned16(dst) && out_plane < (1ll << 31)) {
+    const long long items = out_plane >> 2;
+    // few planes per thread column (grid.y), so that small plane counts still fill the SMs
+    const long long bx4 = (items + threads - 1) / threads;
+    long long by = (16ll * sm_count() + bx4 - 1) / bx4;          // planes per thread = planes / by
+    by = by < 1 ? 1 : (by > planes ? planes : by);
+    if (by > 65535) by = 65535;
+    dim3 grid4(static_cast<unsigned>(bx4), static_cast<unsigned>(by));
+    upsample_bilinear_ac_v4_kernel<NM><<<grid4, threads, 0, st>>>(src, dst, planes, Hin, Win, Hout, Wout,
+                                                                  ac_scale(Hin, Hout), ac_scale(Win, Wout));
+    return check_launch("fuvs_upsample_bilinear_ac");
+  }
   const long long bx = (out_plane + threads - 1) / threads;
   if (bx > 0x7fffffffll) return set_error(FUVS_EINVAL, "upsample: output plane too large");
   dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(planes < 65535 ? planes : 65535));
