@@ -7,6 +7,8 @@
 // (2(n-1) x [C,fh,fw], 265 MB each for DeepLabv3 features at 1080p) and then reads them back for the blend; here the
 // chain states stay at grid resolution and one kernel writes each blended frame straight into its slot of the decoder
 // batch: up-sample of both states + blend per output element, 4 consecutive pixels per thread.
+#include <cstdlib>
+
 #include "fuvs_common.cuh"
 
 namespace fuvs {
@@ -46,6 +48,91 @@ feature_up_blend_kernel(const float* __restrict__ Lst, const float* __restrict__
     }
   }
 }
+
+// Staged variant (fw % 4 == 0): the kernel above issues 8 gather loads per output element (4 taps of each state) and
+// is L1-bound — 1.4 ms for the 1.06 GB of frames 1..n-1 at DeepLabv3 feature size (tools/abi_bench.py).  Here a CTA
+// owns (channel, frame, band of source rows): the HORIZONTAL two-terms of the band's source rows of L_p and R_{n-p}
+// are computed once into shared memory (the op order of UpSample.cuh is horizontal first), and every output row of the
+// band is then one vertical two-term per state on packed FP32x2 straight from 128-bit shared-memory loads, the blend
+// and one streaming 128-bit store — like block_rows.cu, without the arg-max.
+constexpr int FR_THREADS = 256;
+
+__global__ void __launch_bounds__(FR_THREADS, 4)
+feature_rows_kernel(const float* __restrict__ Lst, const float* __restrict__ Rst, float* __restrict__ out, int C, int fh,
+                    int fw, int Hg, int Wg, int n, float sh, float sw, int band_rows, int nbands,
+                    const BlendWeights wts, float one) {
+  extern __shared__ __align__(16) float fr_hs[];            // [state][row of the band + 1][fw]
+  const int tid = threadIdx.x;
+  int idx = blockIdx.x;
+  const int band = idx % nbands;
+  idx /= nbands;
+  const int p = idx % (n - 1) + 1;
+  const int c = idx / (n - 1);
+  const int i_lo = band * band_rows, i_hi = min(Hg, i_lo + band_rows);      // floor source rows [i_lo, i_hi)
+  const int nrows = i_hi - i_lo + 1;                                        // plus the row below the last one
+  const int lplane = Hg * Wg;
+  const long long ls = static_cast<long long>(C) * lplane;
+  const u64 one2 = pack2(one, one);
+  // output rows of the band: floor(sh * y) in [i_lo, i_hi) with the float arithmetic of up_coord()
+  auto src_row = [&](int y) { return static_cast<int>(__fmul_rn(sh, static_cast<float>(y))); };
+  auto first_row_at = [&](int i) {          // smallest y with src_row(y) >= i
+    if (i <= 0) return 0;
+    int y = (sh > 0.f) ? static_cast<int>(static_cast<float>(i) / sh) : fh;
+    y = max(0, min(y, fh));
+    while (y > 0 && src_row(y - 1) >= i) --y;
+    while (y < fh && src_row(y) < i) ++y;
+    return y;
+  };
+  const int y_lo = first_row_at(i_lo), y_hi = (i_hi >= Hg) ? fh : first_row_at(i_hi);
+  if (y_hi <= y_lo) return;
+
+  // ---- phase 1: horizontal two-terms (UpSample.cuh: w0*a + w1*b) of the band's source rows, both states
+  const float* Lp = Lst + (p - 1) * ls + static_cast<long long>(c) * lplane;          // L_p
+  const float* Rp = Rst + (n - p - 1) * ls + static_cast<long long>(c) * lplane;      // R_{n-p}
+  const int per_state = nrows * fw;
+  // a thread owns columns x = tid, tid + 256, ...: one up_coord per column, then a walk down the band's rows
+  // (the first version recomputed the coordinate and an integer division per element and was instruction-bound)
+  for (int x = tid; x < fw; x += FR_THREADS) {
+    const UpCoord wc = up_coord<Nm>(sw, x, Wg);
+    const float* ql = Lp + wc.i0;
+    const float* qr = Rp + wc.i0;
+    float* d = fr_hs + x;
+    for (int r = 0; r < nrows; ++r) {
+      const int off = min(i_lo + r, Hg - 1) * Wg;
+      d[r * fw] = two_term<Nm::kUpInner>(wc.l0, __ldg(ql + off), wc.l1, __ldg(ql + off + wc.ip));
+      d[per_state + r * fw] = two_term<Nm::kUpInner>(wc.l0, __ldg(qr + off), wc.l1, __ldg(qr + off + wc.ip));
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: vertical two-term of both states, blend, store; thread = (group of 4 columns, row phase)
+  const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
+  const int groups = fw >> 2;
+  float* o = out + (static_cast<long long>(p) * C + c) * fh * fw;
+  const int rsplit = max(1, FR_THREADS / groups);
+  for (int g0 = 0; g0 < groups; g0 += FR_THREADS) {            // one pass unless fw > 1024
+    const int lin = tid;
+    const int grp = (groups >= FR_THREADS) ? g0 + lin : lin % groups;
+    const int rphase = (groups >= FR_THREADS) ? 0 : lin / groups;
+    if (grp >= groups || rphase >= rsplit) continue;
+    const int x = grp << 2;
+    for (int y = y_lo + rphase; y < y_hi; y += rsplit) {
+      const UpCoord hc = up_coord<Nm>(sh, y, Hg);
+      const u64 hl0 = pack2(hc.l0, hc.l0), hl1 = pack2(hc.l1, hc.l1);
+      const float* r0 = fr_hs + (hc.i0 - i_lo) * fw + x;
+      const float* r1 = r0 + hc.ip * fw;
+      const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(r0), f1 = *reinterpret_cast<const ulonglong2*>(r1);
+      const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(r0 + per_state), b1 = *reinterpret_cast<const ulonglong2*>(r1 + per_state);
+      const u64 fa = two_term2<Nm::kUpOuter>(hl0, f0.x, hl1, f1.x, one2), fb = two_term2<Nm::kUpOuter>(hl0, f0.y, hl1, f1.y, one2);
+      const u64 ba = two_term2<Nm::kUpOuter>(hl0, b0.x, hl1, b1.x, one2), bb = two_term2<Nm::kUpOuter>(hl0, b0.y, hl1, b1.y, one2);
+      float4 v;
+      unpack2(blend2x2(w0, fa, w1, ba, one2), v.x, v.y);
+      unpack2(blend2x2(w0, fb, w1, bb, one2), v.z, v.w);
+      __stcs(reinterpret_cast<float4*>(o + static_cast<long long>(y) * fw + x), v);
+    }
+  }
+}
+
 
 }  // namespace
 }  // namespace fuvs
@@ -105,6 +192,23 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
       const float sh = fh > 1 ? static_cast<float>(Hg - 1) / (fh - 1) : 0.f;
       const float sw = fw > 1 ? static_cast<float>(Wg - 1) / (fw - 1) : 0.f;
       const bool vec4 = (fw % 4 == 0) && aligned16(out);
+      // staged kernel: bands of source rows sized for four CTAs per SM (2 states x (rows + 1) x fw floats <= 48 KB)
+      static const bool staged = []() { const char* e = getenv("FUVS_FEATURE_STAGED"); return !(e && e[0] == '0'); }();
+      int band_rows = static_cast<int>((48 * 1024) / (8ll * fw)) - 1;
+      if (band_rows > Hg) band_rows = Hg;
+      const long long nb = band_rows >= 1 ? (Hg + band_rows - 1) / band_rows : 0;
+      const long long ctas = nb * C * (n - 1);
+      if (staged && vec4 && band_rows >= 1 && ctas <= 0x7fffffffll && fh > 1 && fw > 1) {
+        const size_t smem = static_cast<size_t>(2) * (band_rows + 1) * fw * sizeof(float);
+        static SmemOptIn optin;
+        if (optin.ensure(feature_rows_kernel, 48 * 1024 + 2 * fw * static_cast<int>(sizeof(float)))) {
+          feature_rows_kernel<<<static_cast<int>(ctas), FR_THREADS, smem, st>>>(Lst, Rst, out, C, fh, fw, Hg, Wg, n, sh, sw,
+                                                                              band_rows, static_cast<int>(nb), w, 1.0f);
+          if (int e = check_launch("fuvs_feature_interval(staged up-sample + blend)")) return e;
+          goto frame0;
+        }
+      }
+      {
       const long long items = static_cast<long long>(C) * fh * (vec4 ? fw / 4 : fw);
       long long grid = (items + 255) / 256;
       const long long cap = 32ll * sm_count();
@@ -114,8 +218,10 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
       else
         feature_up_blend_kernel<1><<<static_cast<int>(grid), 256, 0, st>>>(Lst, Rst, out, C, fh, fw, Hg, Wg, n, sh, sw, w);
       if (int e = check_launch("fuvs_feature_interval(up-sample + blend)")) return e;
+      }
     }
   }
+frame0:
   // frame 0 (flow/model.py:154-159): the key frame's features through the default grid with align_corners=True,
   // restored to the feature size; without a default grid (no_warp) the features themselves
   if (default_grid) {
