@@ -210,6 +210,39 @@ __device__ __forceinline__ float gs_fetch_cg(const float* plane, const GsTap& t,
   return acc;
 }
 
+// All C channels of one grid point: the tap loads of up to 8 channels are issued before the first store.  Written as
+// `dst[c] = gs_fetch_cg(src + c)` the store of channel c — which may alias the source for all the compiler knows (both
+// live in the chain scratch) — keeps the loads of channel c+1 behind it in program order: C dependent L2 round
+// trips per point and step instead of one.
+template <class NM>
+__device__ __forceinline__ void gs_fetch_all_cg(const float* src, long long in_plane, const GsTap& t, int Win, int C,
+                                                float* dst, int out_plane) {
+  const float* p = src + t.off00;
+  const int o01 = t.dx, o10 = t.dy * Win, o11 = t.dy * Win + t.dx;
+  constexpr int U = 8;
+  for (int c0 = 0; c0 < C; c0 += U) {
+    float v00[U], v01[U], v10[U], v11[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u < C) {
+        const float* q = p + (c0 + u) * in_plane;
+        v00[u] = __ldcg(q); v01[u] = __ldcg(q + o01); v10[u] = __ldcg(q + o10); v11[u] = __ldcg(q + o11);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c0 + u < C) {
+        float acc = 0.f;
+        acc = tap_acc<NM>(acc, v00[u], t.nw);
+        if (t.dx) acc = tap_acc<NM>(acc, v01[u], t.ne);
+        if (t.dy) acc = tap_acc<NM>(acc, v10[u], t.sw);
+        if (t.dx & t.dy) acc = tap_acc<NM>(acc, v11[u], t.se);
+        dst[(c0 + u) * out_plane] = acc;
+      }
+    }
+  }
+}
+
 template <class NM>
 __global__ void __cluster_dims__(CHAIN_CLUSTER, 1, 1) __launch_bounds__(CHAIN_THREADS)
 block_chain_cluster_kernel(const float* __restrict__ prev, const float* __restrict__ next,
@@ -231,8 +264,7 @@ block_chain_cluster_kernel(const float* __restrict__ prev, const float* __restri
     for (int pt = crank * CHAIN_THREADS + threadIdx.x; pt < npts; pt += CHAIN_CLUSTER * CHAIN_THREADS) {
       const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
       const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, false);
-#pragma unroll 5
-      for (int c = 0; c < C; ++c) dst[c * npts + pt] = gs_fetch_cg<NM>(src + c * in_plane, t, Win);
+      gs_fetch_all_cg<NM>(src, in_plane, t, Win, C, dst + pt, npts);
     }
     if (j < n - 1) {
       asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -266,8 +298,7 @@ block_chain_coop_kernel(const float* __restrict__ prev, const float* __restrict_
       float* dst = st + (j - 1) * ls;
       const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
       const GsTap tp = gs_setup<NM>(g.x, g.y, Hin, Win, false);
-#pragma unroll 5
-      for (int c = 0; c < C; ++c) dst[c * npts + pt] = gs_fetch_cg<NM>(src + c * in_plane, tp, Win);
+      gs_fetch_all_cg<NM>(src, in_plane, tp, Win, C, dst + pt, npts);
     }
     if (j < n - 1) gridg.sync();
   }
