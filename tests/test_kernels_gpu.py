@@ -337,6 +337,28 @@ def test_confusion_fast_path_edges(cuda, K, pdt, tdt):
         assert np.array_equal(counts.cpu().numpy(), tot)
 
 
+@pytest.mark.parametrize("ignore", [-1, 300, 7])
+def test_confusion_ignore_outside_byte_range(cuda, ignore):
+    """ignore_index values the byte-domain fast path cannot represent (negative, >= 256) or that sit just above the
+    classes: int64 targets holding them must be counted exactly like util/util.py:52-63 does."""
+    K, N = 5, 512 * 37 + 100
+    g = torch.Generator().manual_seed(ignore + 10)
+    pred = torch.randint(0, K, (N,), generator=g)
+    target = torch.randint(0, K, (N,), generator=g)
+    target[torch.rand(N, generator=g) < 0.1] = ignore
+    for pdt in (torch.int64, torch.uint8):
+        if pdt == torch.uint8 and not 0 <= ignore <= 255:
+            continue                            # torch (and numpy) refuse to store such a value in a uint8 tensor
+        p = pred.to(pdt)
+        exp_counts = np.stack(mo.intersection_and_union_histc_ints(p.numpy(), target.numpy(), K, ignore))
+        pc = p.to(cuda)
+        got = kernels.confusion(pc, target.to(cuda), K, ignore, mutate_pred=True).cpu().numpy()
+        assert np.array_equal(got, exp_counts), f"pred {pdt}"
+        exp = p.clone()
+        exp[target == ignore] = ignore
+        assert torch.equal(pc.cpu(), exp)
+
+
 def test_confusion_accumulates_and_ragged(cuda):
     K = 5
     counts = kernels.new_counts(K, cuda)
