@@ -90,17 +90,31 @@ feature_rows_kernel(const float* __restrict__ Lst, const float* __restrict__ Rst
   const float* Lp = Lst + (p - 1) * ls + static_cast<long long>(c) * lplane;          // L_p
   const float* Rp = Rst + (n - p - 1) * ls + static_cast<long long>(c) * lplane;      // R_{n-p}
   const int per_state = nrows * fw;
+  // per output row of the band: {shared-memory offset of source row i0, offset of row i0 + ip, l0, l1}, computed once
+  // per CTA instead of once per 4-pixel item (the coordinate arithmetic with its int<->float conversions was a sixth
+  // of the instructions of this instruction-bound kernel)
+  float4* rowtab = reinterpret_cast<float4*>(fr_hs + 2 * per_state);
+  for (int yy = tid; yy < y_hi - y_lo; yy += FR_THREADS) {
+    const UpCoord hc = up_coord<Nm>(sh, y_lo + yy, Hg);
+    const int o0 = (hc.i0 - i_lo) * fw;
+    rowtab[yy] = make_float4(__int_as_float(o0), __int_as_float(o0 + hc.ip * fw), hc.l0, hc.l1);
+  }
   // a thread owns columns x = tid, tid + 256, ...: one up_coord per column, then a walk down the band's rows
-  // (the first version recomputed the coordinate and an integer division per element and was instruction-bound)
+  // (the first version recomputed the coordinate and an integer division per element)
   for (int x = tid; x < fw; x += FR_THREADS) {
     const UpCoord wc = up_coord<Nm>(sw, x, Wg);
     const float* ql = Lp + wc.i0;
     const float* qr = Rp + wc.i0;
     float* d = fr_hs + x;
+    int row = i_lo;
+#pragma unroll 4
     for (int r = 0; r < nrows; ++r) {
-      const int off = min(i_lo + r, Hg - 1) * Wg;
-      d[r * fw] = two_term<Nm::kUpInner>(wc.l0, __ldg(ql + off), wc.l1, __ldg(ql + off + wc.ip));
-      d[per_state + r * fw] = two_term<Nm::kUpInner>(wc.l0, __ldg(qr + off), wc.l1, __ldg(qr + off + wc.ip));
+      const int off = row * Wg;
+      const float a0 = __ldg(ql + off), a1 = __ldg(ql + off + wc.ip), b0 = __ldg(qr + off), b1 = __ldg(qr + off + wc.ip);
+      d[0] = two_term<Nm::kUpInner>(wc.l0, a0, wc.l1, a1);
+      d[per_state] = two_term<Nm::kUpInner>(wc.l0, b0, wc.l1, b1);
+      d += fw;
+      row = min(row + 1, Hg - 1);
     }
   }
   __syncthreads();
@@ -111,16 +125,17 @@ feature_rows_kernel(const float* __restrict__ Lst, const float* __restrict__ Rst
   float* o = out + (static_cast<long long>(p) * C + c) * fh * fw;
   const int rsplit = max(1, FR_THREADS / groups);
   for (int g0 = 0; g0 < groups; g0 += FR_THREADS) {            // one pass unless fw > 1024
-    const int lin = tid;
-    const int grp = (groups >= FR_THREADS) ? g0 + lin : lin % groups;
-    const int rphase = (groups >= FR_THREADS) ? 0 : lin / groups;
+    const int grp = (groups >= FR_THREADS) ? g0 + tid : tid % groups;
+    const int rphase = (groups >= FR_THREADS) ? 0 : tid / groups;
     if (grp >= groups || rphase >= rsplit) continue;
     const int x = grp << 2;
-    for (int y = y_lo + rphase; y < y_hi; y += rsplit) {
-      const UpCoord hc = up_coord<Nm>(sh, y, Hg);
-      const u64 hl0 = pack2(hc.l0, hc.l0), hl1 = pack2(hc.l1, hc.l1);
-      const float* r0 = fr_hs + (hc.i0 - i_lo) * fw + x;
-      const float* r1 = r0 + hc.ip * fw;
+    const float* hx = fr_hs + x;
+    float* ox = o + static_cast<long long>(y_lo) * fw + x;
+    for (int yy = rphase; yy < y_hi - y_lo; yy += rsplit) {
+      const float4 rt = rowtab[yy];
+      const u64 hl0 = pack2(rt.z, rt.z), hl1 = pack2(rt.w, rt.w);
+      const float* r0 = hx + __float_as_int(rt.x);
+      const float* r1 = hx + __float_as_int(rt.y);
       const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(r0), f1 = *reinterpret_cast<const ulonglong2*>(r1);
       const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(r0 + per_state), b1 = *reinterpret_cast<const ulonglong2*>(r1 + per_state);
       const u64 fa = two_term2<Nm::kUpOuter>(hl0, f0.x, hl1, f1.x, one2), fb = two_term2<Nm::kUpOuter>(hl0, f0.y, hl1, f1.y, one2);
@@ -128,7 +143,7 @@ feature_rows_kernel(const float* __restrict__ Lst, const float* __restrict__ Rst
       float4 v;
       unpack2(blend2x2(w0, fa, w1, ba, one2), v.x, v.y);
       unpack2(blend2x2(w0, fb, w1, bb, one2), v.z, v.w);
-      __stcs(reinterpret_cast<float4*>(o + static_cast<long long>(y) * fw + x), v);
+      __stcs(reinterpret_cast<float4*>(ox + static_cast<long long>(yy) * fw), v);
     }
   }
 }
@@ -194,14 +209,17 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
       const bool vec4 = (fw % 4 == 0) && aligned16(out);
       // staged kernel: bands of source rows sized for four CTAs per SM (2 states x (rows + 1) x fw floats <= 48 KB)
       static const bool staged = []() { const char* e = getenv("FUVS_FEATURE_STAGED"); return !(e && e[0] == '0'); }();
-      int band_rows = static_cast<int>((48 * 1024) / (8ll * fw)) - 1;
+      int band_rows = static_cast<int>((46 * 1024) / (8ll * fw)) - 1;          // 2 KB of the 48 KB for the row table
       if (band_rows > Hg) band_rows = Hg;
-      const long long nb = band_rows >= 1 ? (Hg + band_rows - 1) / band_rows : 0;
+      long long nb = band_rows >= 1 ? (Hg + band_rows - 1) / band_rows : 0;
+      if (nb > 0) band_rows = static_cast<int>((Hg + nb - 1) / nb);            // equal bands
       const long long ctas = nb * C * (n - 1);
       if (staged && vec4 && band_rows >= 1 && ctas <= 0x7fffffffll && fh > 1 && fw > 1) {
-        const size_t smem = static_cast<size_t>(2) * (band_rows + 1) * fw * sizeof(float);
+        // + the row table: a band of band_rows source rows covers at most band_rows (fh-1)/(Hg-1) + 2 output rows
+        const long long mo = (fh > 1 && Hg > 1) ? (static_cast<long long>(band_rows) * (fh - 1) + Hg - 2) / (Hg - 1) + 2 : fh;
+        const size_t smem = static_cast<size_t>(2) * (band_rows + 1) * fw * sizeof(float) + static_cast<size_t>(mo < fh ? mo : fh) * 16;
         static SmemOptIn optin;
-        if (optin.ensure(feature_rows_kernel, 48 * 1024 + 2 * fw * static_cast<int>(sizeof(float)))) {
+        if (smem <= 48 * 1024 && optin.ensure(feature_rows_kernel, 48 * 1024)) {
           feature_rows_kernel<<<static_cast<int>(ctas), FR_THREADS, smem, st>>>(Lst, Rst, out, C, fh, fw, Hg, Wg, n, sh, sw,
                                                                               band_rows, static_cast<int>(nb), w, 1.0f);
           if (int e = check_launch("fuvs_feature_interval(staged up-sample + blend)")) return e;
