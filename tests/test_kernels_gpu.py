@@ -413,6 +413,43 @@ def test_counter_fields_saturate(cuda, n):
         assert np.array_equal(got.cpu().numpy(), ref_counts)
 
 
+@pytest.mark.parametrize("mode", ["linear", "linear_lowres", "dense", "block"])
+def test_interval_entries_replay_from_a_cuda_graph(cuda, mode):
+    """the entry points only enqueue work, so a captured call replays bit-identically.  The block
+    route takes its per-step chain launches while the stream is being captured (the cooperative launch otherwise)."""
+    C, H, W, n = 5, 272, 480, 5
+    o, o_next = keyframe_logits(C, H, W, 3, 0).to(cuda), keyframe_logits(C, H, W, 3, 1).to(cuda)
+    kind = "dense" if mode == "dense" else "block"
+    gl = [g.to(cuda) for g in flow_grids(H, W, n, kind, clip=3, side=0)]
+    gr = [g.to(cuda) for g in flow_grids(H, W, n, kind, clip=3, side=1)]
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(8), dtype=torch.uint8).to(cuda)
+    lo, lo_next = o[:, ::8, ::8].contiguous(), o_next[:, ::8, ::8].contiguous()
+
+    def call(counts):
+        if mode == "linear":
+            return kernels.linear_blend_argmax(o, o_next, n, tc_prev=tc_prev, counts=counts)[0]
+        if mode == "linear_lowres":
+            return kernels.linear_lowres_blend_argmax(lo, lo_next, (H, W), n, tc_prev=tc_prev, counts=counts)[0]
+        if mode == "dense":
+            return kernels.dense_interval(o, o_next, gl, gr, n, tc_prev=tc_prev, counts=counts)[0]
+        return kernels.block_interval(o, o_next, gl, gr, n, tc_prev=tc_prev, counts=counts)[0]
+
+    eager_counts = kernels.new_counts(C, cuda)
+    eager_labels = call(eager_counts).clone()
+    torch.cuda.synchronize()
+    graph_counts = kernels.new_counts(C, cuda)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graph_labels = call(graph_counts)
+    graph_counts.zero_()
+    graph_labels.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(graph_labels, eager_labels)
+    assert torch.equal(graph_counts, 3 * eager_counts)
+
+
 def test_errors_are_loud(cuda):
     with pytest.raises(kernels.FuvsError):
         kernels.linear_blend_argmax(torch.zeros(5, 8, 8), torch.zeros(5, 8, 8), 5)          # CPU tensors
