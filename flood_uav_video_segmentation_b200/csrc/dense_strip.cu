@@ -60,6 +60,7 @@ struct StripGeom {
   int nsx, nby, total, nslot;
   int wl, wr;                                // relative cost of a forward-side / backward-side block (CTA partition)
   int wedge;                                 // cost of a block of the two edge strips, in eighths
+  int wstart;                                // extra cost of the first block of a strip, in eighths of a block
 };
 struct StripMaps {
   CUtensorMap srcL, srcR;                    // [C][H][W] fp32, box BOXW x RB x C
@@ -153,13 +154,22 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
     return (side ? G.wr : G.wl) * (edge ? G.wedge : 8);
   };
+  // A CTA whose range crosses into a new strip has to refill its whole window there (WIN slots = 192 KB instead of
+  // one slot per block): measured, those CTAs ran 11 % longer than the mean and set the launch time
+  // (tools/strip_prof.py).  The first block of every strip therefore carries an extra cost of G.wstart / 8 blocks,
+  // which hands the CTA that owns it correspondingly fewer blocks.
+  auto unit_start = [&](int u) { return (static_cast<long long>(G.wstart) * unit_w(u)) >> 3; };
   long long cost_all = 0;
-  for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u);
+  for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u) + unit_start(u);
   auto block_at = [&](long long num) {        // first block whose start cost is >= num * cost_all / grid
     long long pos = (num * cost_all + gridDim.x - 1) / gridDim.x;
     for (int u = 0; u < 2 * G.nsx; ++u) {
-      const long long w = unit_w(u), cu = static_cast<long long>(G.nby) * w;
-      if (pos <= cu) return u * G.nby + static_cast<int>((pos + w - 1) / w);
+      const long long w = unit_w(u), st = unit_start(u), cu = static_cast<long long>(G.nby) * w + st;
+      if (pos <= cu) {
+        if (pos <= 0) return u * G.nby;
+        const long long k = (pos - st + w - 1) / w;          // block k of the strip starts at cost st + k w (k >= 1)
+        return u * G.nby + static_cast<int>(k < 1 ? 1 : k);
+      }
       pos -= cu;
     }
     return G.total;
@@ -446,6 +456,8 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.wr = 4;
   static const int wedge = []() { const char* e = getenv("FUVS_STRIP_WEDGE"); return e ? atoi(e) : 9; }();
   g.wedge = wedge;
+  static const int wstart = []() { const char* e = getenv("FUVS_STRIP_WSTART"); return e ? atoi(e) : 16; }();   // measured: 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
+  g.wstart = wstart < 0 ? 0 : wstart;
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
   static const bool pdl = []() { const char* e = getenv("FUVS_STRIP_PDL"); return !(e && e[0] == '0'); }();
