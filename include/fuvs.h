@@ -161,6 +161,12 @@ FUVS_API int fuvs_dense_interval(const float* prev, const float* next,
  *
  *   grids_left/right : [n-1,Hg,Wg,2]
  *   scratch          : fuvs_block_scratch_floats(C,Hg,Wg,n) floats
+ *
+ * Like every entry point it only enqueues work on `stream` and may be
+ * captured into a CUDA graph; the chain is one cooperative launch when
+ * enqueued eagerly and n-1 plain launches while `stream` is being captured
+ * (same results; kernel-to-kernel latency inside a graph is below a grid-wide
+ * barrier).
  * ------------------------------------------------------------------------- */
 FUVS_API long long fuvs_block_scratch_floats(int C, int Hg, int Wg, int n);
 FUVS_API int fuvs_block_interval(const float* prev, const float* next,
