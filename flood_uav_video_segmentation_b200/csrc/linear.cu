@@ -117,7 +117,7 @@ linear_blend_argmax_kernel(const float* __restrict__ prev, const float* __restri
 template <int CT, int NP, bool COUNTS, bool NANSAFE, bool LOGITS = true>
 __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 (&b)[CT][NP], long long HW,
                                               long long pix, int n, uint8_t* __restrict__ labels,
-                                              float* __restrict__ logits, bool have_tc, unsigned tc_word,
+                                              float* __restrict__ logits, bool have_tc, typename PixIO<NP>::LabelWord tc_word,
                                               int ignore_index, const BlendWeights& wts, u64 one2,
                                               FieldCounts<CT>& cnt) {
   using FC = FieldCfg<CT>;
@@ -158,7 +158,7 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
           PixIO<NP>::store(logits + c * HW + pix, x);
         }
       }
-      const unsigned w = PixIO<NP>::label_word(idx);
+      const typename PixIO<NP>::LabelWord w = PixIO<NP>::label_word(idx);
       if (labels) PixIO<NP>::store_label_word(labels + pix, w);
       if (COUNTS) {
         unsigned fld[NPX];
@@ -166,7 +166,7 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
         if (have_tc) {                      // tc_word: the callers load it long before it is needed (a DRAM round trip)
 #pragma unroll
           for (int i = 0; i < NPX; ++i) {
-            const int tl = (tc_word >> (8 * i)) & 255u, lab = (w >> (8 * i)) & 255u;
+            const int tl = static_cast<int>((tc_word >> (8 * i)) & 255u), lab = static_cast<int>((w >> (8 * i)) & 255u);
             const unsigned ft = (tl < CT) ? FieldCounts<CT>::field(tl) : 0u;
             // output[target == ignore] = ignore, and ignore is outside [0,CT) on this path: nothing of this pixel counts
             const unsigned fo = (tl == ignore_index) ? 0u : fld[i];
@@ -243,10 +243,10 @@ __device__ __forceinline__ void linear_frames(const u64 (&a)[CT][NP], const u64 
     if (labels) PixIO<NP>::store_labels(labels + pix, lab);
     if (COUNTS) {
       if (have_tc) {                      // tc_word: the callers load it long before it is needed (a DRAM round trip)
-        const unsigned t = tc_word;
+        const typename PixIO<NP>::LabelWord t = tc_word;
 #pragma unroll
         for (int i = 0; i < NPX; ++i) {
-          const int tl = (t >> (8 * i)) & 255u;
+          const int tl = static_cast<int>((t >> (8 * i)) & 255u);
           const unsigned ft = (tl < CT) ? FieldCounts<CT>::field(tl) : 0u;
           // output[target == ignore] = ignore, and ignore is outside [0,CT) on this path: nothing of this pixel counts
           const unsigned fo = (tl == ignore_index) ? 0u : FieldCounts<CT>::field(lab[i]);
@@ -309,7 +309,7 @@ linear_blend_argmax_v4_kernel(const float* __restrict__ prev, const float* __res
     const long long pix = v * NPX;
     u64 a[CT][NP], b[CT][NP];
     const bool have_tc = COUNTS && tc_prev != nullptr;
-    const unsigned tc_word = have_tc ? PixIO<NP>::load_labels(tc_prev + pix) : 0u;
+    const typename PixIO<NP>::LabelWord tc_word = have_tc ? PixIO<NP>::load_labels(tc_prev + pix) : 0u;
 #pragma unroll
     for (int c = 0; c < CT; ++c) PixIO<NP>::load(prev + c * HW + pix, a[c]);
     if (n > 1) {
@@ -445,16 +445,17 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
   // one tile ahead — consumed straight after a load it stalled every warp for a DRAM round trip per tile
   // (long-scoreboard 2.2 warps per issue, profiles/r01_ncu_linear_final.txt)
   const bool have_tc = COUNTS && tc_prev != nullptr;
-  auto tc_load = [&](long long tile) -> unsigned {
+  using LabelWord = typename PixIO<NP>::LabelWord;
+  auto tc_load = [&](long long tile) -> LabelWord {
     const long long px = tile * BULK_TILE + tid * NPX;
-    return (have_tc && px < HW) ? PixIO<NP>::load_labels(tc_prev + px) : 0u;
+    return (have_tc && px < HW) ? PixIO<NP>::load_labels(tc_prev + px) : LabelWord(0);
   };
-  unsigned tc_word = tc_load(blockIdx.x);
+  LabelWord tc_word = tc_load(blockIdx.x);
   for (long long i = 0;; ++i) {
     const long long t = blockIdx.x + i * gridDim.x;
     if (t >= ntiles) break;
     if (t * BULK_TILE + q * BULK_QPX >= HW) break;              // this quarter of the last tile is past the end: no load was issued
-    const unsigned tc_next = tc_load(t + gridDim.x);
+    const LabelWord tc_next = tc_load(t + gridDim.x);
     const int s = static_cast<int>(i % BULK_STAGES);
     lin_wait(lin_smem_u32(&bars[s * BULK_NQ + q]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
     const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * NPX;
@@ -462,7 +463,13 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
     const bool live = pix < HW;                                  // HW % 4 == 0: a thread's 4 pixels are all in or all out
     u64 a[CT][NP], b[CT][NP];
     auto lds = [&](const float* p, u64 (&d)[NP]) {
-      if constexpr (NP == 2) {
+      if constexpr (NP == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p), u = *(reinterpret_cast<const float4*>(p) + 1);
+        d[0] = pack2(v.x, v.y);
+        d[1] = pack2(v.z, v.w);
+        d[2] = pack2(u.x, u.y);
+        d[3] = pack2(u.z, u.w);
+      } else if constexpr (NP == 2) {
         const float4 v = *reinterpret_cast<const float4*>(p);
         d[0] = pack2(v.x, v.y);
         d[1] = pack2(v.z, v.w);
@@ -555,6 +562,8 @@ static int launch_bulk(const float* prev, const float* next, long long HW, int n
   static const int px = linear_env("FUVS_LINEAR_BULK_PX", 4);       // 4 pixels x 512 threads | 2 pixels x 1024 threads
   if (nq == 4) return launch_bulk_nq<CT, COUNTS, LOGITS, 4, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
   if (px == 2) return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 1>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  if (px == 8 && HW % 8 == 0 && aligned8(labels) && aligned8(tc_prev) && (!logits || aligned16(logits)))
+    return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 4>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
   return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
 }
 

@@ -87,6 +87,7 @@ __device__ __forceinline__ unsigned one_shl_wrap(unsigned c) {
 //                            NP = 1 -> 2 pixels (64-bit loads, 16-bit label stores; half the registers, twice the warps)
 template <int NP> struct PixIO;
 template <> struct PixIO<2> {
+  using LabelWord = unsigned;
   static __device__ __forceinline__ void load(const float* p, u64 (&d)[2]) {
     const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
     d[0] = pack2(t.x, t.y);
@@ -110,6 +111,7 @@ template <> struct PixIO<2> {
   static __device__ __forceinline__ void store_label_word(uint8_t* p, unsigned w) { *reinterpret_cast<unsigned*>(p) = w; }
 };
 template <> struct PixIO<1> {
+  using LabelWord = unsigned;
   static __device__ __forceinline__ void load(const float* p, u64 (&d)[1]) {
     const float2 t = __ldcs(reinterpret_cast<const float2*>(p));
     d[0] = pack2(t.x, t.y);
@@ -130,6 +132,31 @@ template <> struct PixIO<1> {
   static __device__ __forceinline__ void store_label_word(uint8_t* p, unsigned w) {
     *reinterpret_cast<unsigned short*>(p) = static_cast<unsigned short>(w);
   }
+};
+
+// 8 pixels per thread (two 128-bit loads per plane, one 64-bit label store): measured variant of the bulk linear kernel
+template <> struct PixIO<4> {
+  using LabelWord = unsigned long long;
+  static __device__ __forceinline__ void load(const float* p, u64 (&d)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p)), u = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+    d[0] = pack2(t.x, t.y); d[1] = pack2(t.z, t.w); d[2] = pack2(u.x, u.y); d[3] = pack2(u.z, u.w);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&x)[8]) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3]));
+    __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(x[4], x[5], x[6], x[7]));
+  }
+  static __device__ __forceinline__ void store_labels(uint8_t* p, const int (&l)[8]) {
+    unsigned long long w = 0ull;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w |= static_cast<unsigned long long>(static_cast<unsigned>(l[i]) & 255u) << (8 * i);
+    *reinterpret_cast<unsigned long long*>(p) = w;
+  }
+  static __device__ __forceinline__ LabelWord load_labels(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned long long*>(p)); }
+  static __device__ __forceinline__ LabelWord label_word(const u64 (&idx)[4]) {
+    const u64 lo[2] = {idx[0], idx[1]}, hi[2] = {idx[2], idx[3]};
+    return static_cast<unsigned long long>(PixIO<2>::label_word(lo)) | (static_cast<unsigned long long>(PixIO<2>::label_word(hi)) << 32);
+  }
+  static __device__ __forceinline__ void store_label_word(uint8_t* p, LabelWord w) { *reinterpret_cast<unsigned long long*>(p) = w; }
 };
 
 }  // namespace fuvs
