@@ -59,7 +59,7 @@ __device__ int g_strip_dbg;   // bit 0: no tap loads, 1: no state stores, 2: fix
 struct StripGeom {
   int nsx, nby, total, nslot;
   int wl, wr;                                // relative cost of a forward-side / backward-side block (CTA partition)
-  int wedge;                                 // cost of a block of the two edge strips, in eighths
+  int wedge;                                 // cost of a block of the two edge strips, in sixteenths
   int wstart;                                // extra cost of the first block of a strip, in eighths of a block
 };
 struct StripMaps {
@@ -152,7 +152,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     const bool side = u >= G.nsx;
     const int strip = side ? u - G.nsx : u;
     const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
-    return (side ? G.wr : G.wl) * (edge ? G.wedge : 8);
+    return (side ? G.wr : G.wl) * (edge ? G.wedge : 16);
   };
   // A CTA whose range crosses into a new strip has to refill its whole window there (WIN slots = 192 KB instead of
   // one slot per block): measured, those CTAs ran 11 % longer than the mean and set the launch time
@@ -452,9 +452,10 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.nby = (H + RB - 1) / RB;
   g.total = 2 * g.nsx * g.nby;
   g.nslot = nslot;
-  g.wl = KEY0 ? 5 : 4;                         // measured: frame 0 costs the forward side ~25 % more per block
-  g.wr = 4;
-  static const int wedge = []() { const char* e = getenv("FUVS_STRIP_WEDGE"); return e ? atoi(e) : 9; }();
+  static const int wkey0 = []() { const char* e = getenv("FUVS_STRIP_WKEY0"); return e ? atoi(e) : 9; }();
+  g.wl = KEY0 ? wkey0 : 8;                     // measured (eighths): 8 -> 244.6, 9 -> 242.7, 10 -> 245.3, 11 -> 247.6 us per interval
+  g.wr = 8;
+  static const int wedge = []() { const char* e = getenv("FUVS_STRIP_WEDGE"); return e ? atoi(e) : 18; }();   // sixteenths
   g.wedge = wedge;
   static const int wstart = []() { const char* e = getenv("FUVS_STRIP_WSTART"); return e ? atoi(e) : 16; }();   // measured: 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
   g.wstart = wstart < 0 ? 0 : wstart;
