@@ -481,24 +481,84 @@ def time_stock_torch(mode, clip, device, intervals=6, rounds=3):
     return best, labels
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+# ----------------------------------------------------------------------------- CPU baseline (reference / oracle port)
+class _NullProfiler:
+    """Lightning's profiler as the reference uses it: profiler.profile(name) context managers (flow/model.py:119-232)."""
+
+    def profile(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def load_reference():
+    """The reference's own modules, copied unmodified to oracle/_ref by oracle/make_ref.py (None when absent)."""
+    if load_reference.cache is False:
+        try:
+            from oracle import make_ref
+            load_reference.cache = make_ref.load()
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] oracle/_ref not usable ({exc!r}); CPU baseline falls back to the oracle port", file=sys.stderr)
+            load_reference.cache = None
+    return load_reference.cache
+
+
+load_reference.cache = False
+
+
+def cpu_kind():
+    return "reference" if load_reference() is not None else "port"
+
+
 def cpu_interval(mode, keys, grids, it, last):
-    """The reference call sequence on torch-CPU: FlowModel.predict -> max(1)[1] -> uint8 -> numpy temporal IoU."""
-    from oracle import flow_oracle as fo
-    from oracle import metric_oracle as mo
-    ident = torch.nn.Identity()
+    """One interval on torch-CPU: FlowModel.predict -> max(1)[1] -> uint8 -> temporal-consistency counts.
+
+    With oracle/_ref present this executes the reference's own FlowModel.predict (flow/model.py:109-249) and
+    intersectionAndUnion (util/util.py:36-47); the ~15 lines of flow/base.py:276-295 around them (arg-max, uint8 cast,
+    the temporal loop through compute_metrics' CPU branch, base/foundation.py:333-339) are restated here because
+    flow/base.py needs pytorch_lightning.  Without oracle/_ref the oracle port does the same (kind "port")."""
     n = K_DELTA
     if mode == "linear":
         gl = gr = [torch.zeros(1, 1)] * (n - 1)
     else:
         gl = [grids[it][0][j:j + 1] for j in range(n - 1)]
         gr = [grids[it][1][j:j + 1] for j in range(n - 1)]
+    ref = load_reference()
+    if ref is None:
+        from oracle import flow_oracle as fo
+        from oracle import metric_oracle as mo
+        ident = torch.nn.Identity()
+        with torch.no_grad():
+            logits = fo.predict_segmentation(ident, ident, keys[it], keys[it + 1], gl, gr, n, no_warp=(mode == "linear"))
+            labels = fo.argmax_labels(logits)
+        lab_np = labels.numpy().astype("uint8")
+        counts, new_last = mo.temporal_consistency_counts(labels.numpy(), keys[it].shape[1], 255, last)
+        return lab_np, counts, new_last
+    from types import SimpleNamespace
+    model = cpu_interval.models.get(mode)
+    if model is None:
+        net = SimpleNamespace(encoder=torch.nn.Identity(), decoder=torch.nn.Identity())
+        model = cpu_interval.models[mode] = ref["FlowModel"](net, feature_based=False, no_warp=(mode == "linear")).eval()
+    classes = keys[it].shape[1]
     with torch.no_grad():
-        logits = fo.predict_segmentation(ident, ident, keys[it], keys[it + 1], gl, gr, n, no_warp=(mode == "linear"))
-        labels = fo.argmax_labels(logits)
-    lab_np = labels.numpy().astype("uint8")
-    counts, new_last = mo.temporal_consistency_counts(labels.numpy(), C, 255, last)
-    return lab_np, counts, new_last
+        output = model.predict(keys[it], keys[it + 1], gl, gr, n, _NullProfiler())["pred"]     # flow/base.py:271
+        output = output.data.max(1)[1]                                                         # :276
+        output_numpy = output.data.cpu().numpy().astype("uint8")                               # :277
+    tot = [np.zeros(classes, np.int64) for _ in range(3)]
+    for p in range(n):                                                                         # :280-295
+        if p > 0:
+            cur, nxt = output[p], output[p - 1]
+        elif last is not None:
+            cur, nxt = output[p], last
+        else:
+            continue
+        i, u, t = ref["intersectionAndUnion"](cur.unsqueeze(0).detach().numpy(), nxt.unsqueeze(0).detach().numpy(),
+                                              classes, 255)                                    # foundation.py:334-339
+        for acc, v in zip(tot, (i, u, t)):
+            acc += v
+    return output_numpy, tuple(tot), output[n - 1]
+
+
+cpu_interval.models = {}
 
 
 def time_cpu(mode, host_clip, intervals, warm=1):

@@ -84,22 +84,38 @@ class DeviceMeter:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.counts = kernels.new_counts(classes, self.device)
         self.updates = 0
+        self._reduced = False
 
     def reset(self):
         self.counts.zero_()
         self.updates = 0
+        self._reduced = False
 
     def update(self, output, target, ignore_index=255):
         """One compute_metrics(...) + three AverageMeter.update(...) of the reference, without leaving the device."""
+        if getattr(self, "_reduced", False):
+            raise kernels.FuvsError("DeviceMeter.update after all_reduce: reset() the meter at the start of the next epoch")
         kernels.confusion(output, target, self.classes, ignore_index, counts=self.counts,
                           mutate_pred=output.is_contiguous())
         self.updates += 1
 
+    def note_updates(self, steps):
+        """Metric calls that were fused into an interval kernel (FlowBaseModel.predict_step) count like update()."""
+        self.updates += max(int(steps), 0)
+
     def all_reduce(self):
-        """Single NCCL all-reduce (sum, int64, 3K values) over the job."""
+        """Single NCCL all-reduce (sum, int64, 3K + 1 values) over the job: the counts and the number
+        of metric updates travel together, so a rank that saw no interval still reports the job's metrics.  Idempotent
+        within an epoch: a second call returns the already reduced counts instead of summing them again."""
         import torch.distributed as dist
+        if getattr(self, "_reduced", False):
+            return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.counts, op=dist.ReduceOp.SUM)
+            buf = torch.cat([self.counts.reshape(-1), torch.tensor([self.updates], dtype=torch.int64, device=self.device)])
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            self.counts.copy_(buf[:-1].reshape(self.counts.shape))
+            self.updates = int(buf[-1].item())
+        self._reduced = True
         return self
 
     def to_meters(self):

@@ -3,25 +3,39 @@
 // Why: the per-plane TMA kernel (dense_tma.cu) stages, for every 128x16 output tile, a 192x48 source box per channel:
 // every source byte crosses the L2->SM fabric 4.5 times (409 MB per step at 1080p, profiles/r01_ncu_dense_tma_v5.txt),
 // which is what bounds it.  Here a CTA owns a run of consecutive 8-row blocks of one 128-pixel column strip and keeps
-// the source window of ALL channels resident in shared memory as a ring of 8-row slots.  Moving one block down the
-// strip costs one new slot (192 x 8 x C floats, one cp.async.bulk.tensor.3d), so a source byte crosses the fabric
-// ~1.5 times (x-halo only) plus a 32-row warm-up per run.
+// the source window of ALL channels resident in shared memory as a ring of rows.  Moving one block down the strip
+// costs 8 new rows per channel, so a source byte crosses the fabric ~1.5 times (x-halo only) plus a 32-row warm-up per
+// run.
 //
 //   work     : 2 sides x ceil(W/128) strips x ceil(H/8) blocks, numbered side-major/strip/row; CTA b of a persistent
-//              grid (one CTA per SM) takes the contiguous range [b*T/G, (b+1)*T/G).  A range may cross a strip
-//              boundary: it is then processed as several "segments", each with its own window warm-up.
-//   ring     : NS slots (7 for C=5: 215 KB).  A block needs the 5 slots covering rows [y0-16, y0+24); the others are
-//              prefetched slots of the following blocks.  Slot loads are numbered s = 0,1,2.. in the order of use;
-//              load s lives in buffer s % NS and completes phase (s / NS) & 1 of mbarrier full[s % NS].
-//   protocol : no block-wide barrier.  A warp that has finished block k bumps done[k & 3]; the LAST warp to do so
-//              knows which slot loads are now dead and issues the loads that reuse their buffers.
-//   taps     : shared-memory loads with immediate channel offsets; a warp whose taps leave the window (large motion)
-//              gathers its pixels of that block from global memory instead, so any flow field stays correct.
-//   counts   : stay in fuvs_temporal_counts (metric.cu).  Fusing them into the last step was measured: the byte-wide
-//              label re-reads and ~40 extra instructions per pixel cost 38 us against 15 us for the separate kernel.
+//              grid (one CTA per SM) takes a contiguous cost-weighted range.  A range may cross a strip boundary: it
+//              is then processed as several "segments", each with its own window warm-up.
+//   ring     : per channel NS*8 rows of 192 floats (NS = 7 slots of 8 rows for C=5: 215 KB), channel-major
+//              [c][ring row][x], so that a tap address is ring_row*192 + x with the channel as an immediate offset
+//              and the row below is +192 except at the wrap.  A block needs the 5 slots covering rows
+//              [y0-16, y0+24); the others are prefetched slots of the following blocks.  Slot loads are numbered
+//              s = 0,1,2.. in the order of use; load s lives in slot s % NS and completes phase (s / NS) & 1 of
+//              mbarrier full[s % NS] (C cp.async.bulk.tensor copies of 192 x 8 floats, one per channel).
+//   protocol : no block-wide barrier.  A warp that has finished block k bumps done[k & 3] (counters only grow, so there
+//              is no reset to race with); the LAST warp to do so knows which slot loads are now dead and issues the
+//              loads that reuse their rows.  The counter's old value returns through the MIO queue behind the gathers
+//              of the other warps, so it is looked at only after the coordinates of the next block are computed
+//              (measured r02: the warp used to sit 8 % of its time on that round trip and the fence in front of it).
+//   registers: flow vectors are prefetched two blocks ahead and the pointwise operand of emitting steps one block
+//              ahead into two alternating register sets (the block loop is unrolled by two), so no register move
+//              waits for a load in the iteration that issued it.
+//   body     : (r02) per block and thread: coordinates and weights of its two pixels from registers, then ALL tap
+//              loads of both pixels in one burst of volatile ld.shared (one round trip through the shared-memory
+//              pipe per block instead of the four dependent ones ptxas produced when it sank loads under the store
+//              predicates), then the FMA chains, blends and stores.  Full-size shapes (W % 128 == 0, H % 8 == 0)
+//              compile without per-pixel validity predicates.
+//   taps     : a warp whose taps leave the window (large motion) gathers its pixels of that block from global memory
+//              instead, so any flow field stays correct.
+//   counts   : stay in fuvs_temporal_counts (metric.cu).
 // Arithmetic is gs_setup/tap_acc/blend2 from fuvs_common.cuh: bit-identical to the direct kernel (warp.cu) and to
 // ATen's grid_sampler_2d (flow/model.py:244-249).
-#include <cstdlib>
+#include <type_traits>
+#include <utility>
 
 #include "dense_common.cuh"
 #include "tma_ptx.cuh"
@@ -33,10 +47,13 @@ namespace {
 using namespace tma;
 
 constexpr int TW = 128;                      // strip width = threads per thread-row
+constexpr int TROWS = 4;                     // thread rows; a thread owns rows ty and ty + 4 of a block
+constexpr int PX = 2;
+constexpr int THREADS = TW * TROWS;
+constexpr int NWARPS = THREADS / 32;
 constexpr int HALO_X = 32, HALO_Y = 16;
 // Row stride 192 = 0 mod 32 banks on purpose: with coherent flow a warp's taps straddle at most two rows and stay
-// conflict-free whatever the rows are.  A skewed stride (196) was measured: it spreads the taps that border clipping
-// sends to one column (edge strips, iid flow: -1 %) but costs coherent flow 5 % (2-way conflicts at row changes).
+// conflict-free whatever the rows are (a skewed stride was measured in r01: iid flow -1 %, coherent flow +5 %).
 constexpr int BOXW = TW + 2 * HALO_X;        // 192
 constexpr int RB = 8;                        // rows per block = rows per ring slot
 constexpr int WIN = (RB + 2 * HALO_Y) / RB;  // 5 slots cover the window of one block
@@ -49,13 +66,6 @@ constexpr int nslot_for(int C) {
 }
 constexpr int NSLOT_C2 = nslot_for(2), NSLOT_C5 = nslot_for(5);   // 8, 7
 
-#ifdef FUVS_STRIP_PROF
-// developer instrumentation (not in the product build): per CTA, cycles thread 0 spent waiting for the ring vs in total
-__device__ unsigned long long g_strip_prof[16 * 148 * 4];
-__device__ unsigned g_strip_launch;
-__device__ int g_strip_dbg;   // bit 0: no tap loads, 1: no state stores, 2: fixed taps, 3: no TMA / ring waits, 4: no grid loads
-#endif
-
 struct StripGeom {
   int nsx, nby, total, nslot;
   int wl, wr;                                // relative cost of a forward-side / backward-side block (CTA partition)
@@ -63,21 +73,42 @@ struct StripGeom {
   int wstart;                                // extra cost of the first block of a strip, in eighths of a block
 };
 struct StripMaps {
-  CUtensorMap srcL, srcR;                    // [C][H][W] fp32, box BOXW x RB x C
+  CUtensorMap srcL, srcR;                    // [C][H][W] fp32, box BOXW x RB x 1
 };
 
-template <int PX>
-struct BlockTaps {
-  int aN[PX], aS[PX];                        // float offsets of the nw / sw taps inside the ring
-  float wnw[PX], wne[PX], wsw[PX], wse[PX];
-  unsigned dxm, dym, valid;
-};
+template <int... I, class F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F&& f) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  static_for_impl(std::make_integer_sequence<int, N>{}, f);
+}
+
+// volatile: ptxas keeps these in program order and cannot sink them under a later predicate
+template <int OFF>
+__device__ __forceinline__ float lds_imm(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ float lds_rt(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+// Relaxed on purpose: every ring read of the calling warp has been consumed by an FMA before this instruction issues
+// (an SM issues a warp's instructions in order), so there is nothing a release fence would still have to wait for — a
+// fence here would wait for the warp's global stores and prefetches instead.  The winner fences before it refills.
+__device__ __forceinline__ unsigned atom_add_relaxed(uint32_t addr, unsigned v) {
+  unsigned old;
+  asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 
 // Rare path: the warp computes its pixels of this block straight from global memory (same math as warp.cu).
-// Returns the labels of the PX pixels packed 8 bits each (emitted frame; frame 0 for KEY0 launches).
-template <class NM, int PX, int TROWS>
-__device__ __noinline__ unsigned block_from_global(const DenseStep* __restrict__ Ap, bool side, bool emit, bool key0,
-                                                   int C, int H, int W, int x, int ytop, unsigned valid) {
+__device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap, bool side, bool emit, bool key0, int C,
+                                               int H, int W, int x, int ytop, unsigned valid) {
   const DenseStep& A = *Ap;
   const long long HW = static_cast<long long>(H) * W;
   const float* grid = side ? A.gridR : A.gridL;
@@ -87,22 +118,21 @@ __device__ __noinline__ unsigned block_from_global(const DenseStep* __restrict__
   const float w_this = side ? A.wB1 : A.wA0, w_point = side ? A.wB0 : A.wA1;
   uint8_t* lab_out = side ? A.labelB : A.labelA;
   float* logit_out = side ? A.logitB : A.logitA;
-  unsigned packed = 0u;
   for (int r = 0; r < PX; ++r) {
     if (!((valid >> r) & 1u)) continue;
     const long long pix = static_cast<long long>(ytop + r * TROWS) * W + x;
     const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pix);
-    const GsTap t = gs_setup<NM>(g.x, g.y, H, W, false);
+    const GsTap t = gs_setup<Nm>(g.x, g.y, H, W, false);
     ArgMax am, am0;
     am.init(-INFINITY);
     am0.init(-INFINITY);
     for (int c = 0; c < C; ++c) {
       const long long o = c * HW + pix;
-      const float acc = gs_fetch<NM>(src + c * HW, t, W);
+      const float acc = gs_fetch<Nm>(src + c * HW, t, W);
       if (dst) dst[o] = acc;
       if (emit) {
         const float other = __ldg(point + o);
-        const float v = side ? blend2(w_point, other, w_this, acc) : blend2(w_this, acc, w_point, other);
+        const float v = blend2(w_this, acc, w_point, other);
         am.push(v, c);
         if (logit_out) __stcs(logit_out + o, v);
       }
@@ -114,33 +144,34 @@ __device__ __noinline__ unsigned block_from_global(const DenseStep* __restrict__
     }
     if (emit && lab_out) lab_out[pix] = static_cast<uint8_t>(am.idx);
     if (key0 && A.label0) A.label0[pix] = static_cast<uint8_t>(am0.idx);
-    packed |= static_cast<unsigned>(emit ? am.idx : am0.idx) << (8 * r);
   }
-  return packed;
 }
 
 //   EMIT   : both sides complete a frame this step (blend with the other chain's state read pointwise, arg-max)
 //   KEY0   : step 1: the forward side also emits frame 0 = arg-max of the key frame (read from the ring itself)
+//   WDST   : the step writes its states (every step but the last)
+//   FULLV  : W % 128 == 0 and H % 8 == 0: every pixel of every block exists
 //   NSC    : ring slots when known at compile time (0: G.nslot)
-template <class NM, int CT, int NSC, int TROWS, bool EMIT, bool KEY0>
-__global__ void __launch_bounds__(TW * TROWS, 1)
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV>
+__global__ void __launch_bounds__(THREADS, 1)
 dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
                    StripGeom G) {
   static_assert(!(EMIT && KEY0), "frame 0 and a completed frame never share a step here (the host routes n<=2 elsewhere)");
-  constexpr int THREADS = TW * TROWS;
-  constexpr int PX = RB / TROWS;
-  constexpr int NWARPS = THREADS / 32;
   constexpr int CR = CT > 0 ? CT : 1;
-  constexpr bool FULLV = false;   // pixel validity is tested per store (partial strips / blocks at the image edge)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : Crt;
-  const int slot_floats = C * PLANE;
-  const uint32_t slot_bytes = static_cast<uint32_t>(slot_floats) * 4u;
   const int NS = NSC > 0 ? NSC : G.nslot;
+  const int NSR = NS * RB;                                             // ring rows per channel
+  const int chan_floats = NSR * BOXW;
+  const uint32_t slot_bytes = static_cast<uint32_t>(C) * PLANE * 4u;
   float* bufs = reinterpret_cast<float*>(smem_raw);
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + static_cast<size_t>(NS) * slot_bytes);
-  unsigned* done = reinterpret_cast<unsigned*>(bars + MAX_SLOTS);     // 4 counters
-  const uint32_t bar0 = smem_u32(bars);
+  // 64 bytes of pad behind the ring: the (never accumulated) east tap of a pixel clipped to the last window column of
+  // the last ring row must not alias the barrier words
+  unsigned long long* bars =
+      reinterpret_cast<unsigned long long*>(smem_raw + static_cast<size_t>(C) * chan_floats * sizeof(float) + 64);
+  const uint32_t bar0 = smem_u32(bars);                               // full[MAX_SLOTS]
+  const uint32_t done0 = bar0 + 8u * MAX_SLOTS;                       // done[4] block-completion counters
+  const uint32_t ring0 = smem_u32(bufs);
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int tx = tid & (TW - 1), ty = tid >> 7;                        // TW == 128
@@ -154,10 +185,8 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
     return (side ? G.wr : G.wl) * (edge ? G.wedge : 16);
   };
-  // A CTA whose range crosses into a new strip has to refill its whole window there (WIN slots = 192 KB instead of
-  // one slot per block): measured, those CTAs ran 11 % longer than the mean and set the launch time
-  // (tools/strip_prof.py).  The first block of every strip therefore carries an extra cost of G.wstart / 8 blocks,
-  // which hands the CTA that owns it correspondingly fewer blocks.
+  // A CTA whose range crosses into a new strip has to refill its whole window there: the first block of every strip
+  // carries an extra cost of G.wstart / 8 blocks, which hands the CTA that owns it correspondingly fewer blocks.
   auto unit_start = [&](int u) { return (static_cast<long long>(G.wstart) * unit_w(u)) >> 3; };
   long long cost_all = 0;
   for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u) + unit_start(u);
@@ -177,66 +206,77 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
   const int B0 = block_at(blockIdx.x);
   const int B1 = (blockIdx.x + 1 == gridDim.x) ? G.total : block_at(blockIdx.x + 1);
 
-#ifdef FUVS_STRIP_PROF
-  const int dbg0 = g_strip_dbg;
-#else
-  constexpr int dbg0 = 0;
-#endif
   // Programmatic dependent launch: this CTA may have been scheduled while the previous kernel of the stream (the
   // step that produced our source states) is still draining.  Let our own successor do the same, set up the
   // barriers, then wait for the predecessor's memory to be complete before the first global access.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int b = 0; b < MAX_SLOTS; ++b) mbar_init(bar0 + 8u * b, 1);
-    for (int b = 0; b < 4; ++b) done[b] = 0u;
+    for (int b = 0; b < 4; ++b) reinterpret_cast<unsigned*>(bars + MAX_SLOTS)[b] = 0u;
     fence_barrier_init();
   }
   __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // Left edge of a strip's window.  Kept inside the image where the image is wide enough: a box that hangs over
-  // the image edge is zero-filled by TMA but loads far slower (measured: the CTAs of the last strip waited 50k
-  // cycles per launch for their ring), and border clipping never reads beyond the edge anyway.
+  // the image edge is zero-filled by TMA but loads far slower, and border clipping never reads beyond the edge.
   auto box_x = [&](int strip) { return max(0, min(strip * TW - HALO_X, W - BOXW)); };
-  // one thread: start slot load s of this CTA's sequence (its buffer is known to be dead)
-  auto issue = [&](int s) {
-    int kb = B0, sb = 0;
-    while (kb < B1) {
-      const int u = kb / G.nby, j0 = kb - u * G.nby;
-      const int nb = min(G.nby - j0, B1 - kb);
-      if (s < sb + nb + WIN - 1) {
-        const int ytop = (j0 + (s - sb)) * RB - HALO_Y;
-        const bool side = u >= G.nsx;
-        const int strip = side ? u - G.nsx : u;
-        const int b = s % NS;
-        const uint32_t bar = bar0 + 8u * b;
-        if (ytop + RB <= 0 || ytop >= H || (dbg0 & 8)) {
-          mbar_arrive(bar);                    // slot entirely outside the image: never read (border clipping)
-        } else {
-          mbar_expect_tx(bar, slot_bytes);
-          load_3d(smem_u32(bufs + static_cast<size_t>(b) * slot_floats), side ? &M.srcR : &M.srcL, box_x(strip), ytop, 0,
-                  bar);
-        }
-        return;
-      }
+  // Segments of this CTA's range [B0, B1): the first starts at block J00 of unit U0, the following ones at block 0 of
+  // the next units.  visit(u, j0, nb, sb, k0) gets the unit, its first block, the number of blocks, the index of the
+  // segment's first slot load and the CTA-local index of its first block; returning true ends the walk.
+  const int U0 = B0 / G.nby, J00 = B0 - U0 * G.nby;
+  auto walk = [&](auto&& visit) {
+    int u = U0, j0 = J00, left = B1 - B0, sb = 0, k0 = 0;
+    while (left > 0) {
+      const int nb = min(G.nby - j0, left);
+      if (visit(u, j0, nb, sb, k0)) return;
       sb += nb + WIN - 1;
-      kb += nb;
+      k0 += nb;
+      left -= nb;
+      ++u;
+      j0 = 0;
     }
+  };
+  // one thread: start slot load s of this CTA's sequence (its rows are known to be dead)
+  auto issue = [&](int s) {
+    walk([&](int u, int j0, int nb, int sb, int) {
+      if (s >= sb + nb + WIN - 1) return false;
+      const int ytop = (j0 + (s - sb)) * RB - HALO_Y;
+      const bool side = u >= G.nsx;
+      const int strip = side ? u - G.nsx : u;
+      const int b = s % NS;
+      const uint32_t bar = bar0 + 8u * b;
+      if (ytop + RB <= 0 || ytop >= H) {
+        mbar_arrive(bar);                    // slot entirely outside the image: never read (border clipping)
+      } else {
+        mbar_expect_tx(bar, slot_bytes);
+        const uint32_t dst = ring0 + static_cast<uint32_t>(b * PLANE) * 4u;
+        const int bx = box_x(strip);
+        for (int c = 0; c < C; ++c)
+          load_3d(dst + static_cast<uint32_t>(c * chan_floats) * 4u, side ? &M.srcR : &M.srcL, bx, ytop, c, bar);
+      }
+      return true;
+    });
   };
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) issue(s);
   }
-
-#ifdef FUVS_STRIP_PROF
-  long long prof_wait = 0, prof_first = 0;
-  const unsigned prof_launch = *reinterpret_cast<volatile unsigned*>(&g_strip_launch) & 15u;
-  const long long prof_t0 = clock64();
-#endif
-
-  int kb = B0, sb = 0, kglob = 0, released = 0;
-  while (kb < B1) {                              // ---- one segment: nb consecutive blocks of one (side, strip)
-    const int u = kb / G.nby, j0 = kb - u * G.nby;
-    const int nb = min(G.nby - j0, B1 - kb);
+  const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
+  const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
+  int u = U0, j0 = J00, left = B1 - B0, sb = 0, kglob = 0, released = 0;
+  // lane 0 of every warp: old value of the completion counter of the block it finished last, and what to refill if
+  // that value says it was the last warp (checked after the next block's coordinates, see `protocol` above)
+  unsigned tok = 0u, tok_want = 1u;
+  int tok_from = 0, tok_to = 0;
+  auto refill_if_last = [&]() {
+    if (lane == 0 && tok == tok_want) {
+      __threadfence_block();                       // winner only: acquire side of the hand-over
+      for (int s = tok_from + NS; s < tok_to + NS; ++s) issue(s);
+    }
+    tok_want = tok + 1u;                           // checked once
+  };
+  while (left > 0) {                             // ---- one segment: nb consecutive blocks of one (side, strip)
+    const int nb = min(G.nby - j0, left);
     const bool side = u >= G.nsx;
     const int strip = side ? u - G.nsx : u;
     const int x0 = strip * TW, xbase = box_x(strip);
@@ -250,16 +290,15 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     float* logit_out = side ? A.logitB : A.logitA;
     const bool do_key0 = KEY0 && !side;
     const int rstride = TROWS * W;
-    const bool vx = x < W;
+    const bool vx = FULLV || x < W;
+    const int kx = -0x4B000000 - xbase;            // window column of a tap: mantissa bits of (ix + 2^23) + kx
+    const uint32_t colbase = ring0 + static_cast<uint32_t>(min(x, W - 1) - xbase) * 4u;   // this thread's own column
 
-    // Flow vectors are prefetched TWO blocks ahead and the pointwise operand of emitting steps ONE block ahead: a
-    // block takes ~2.5k cycles, less than a loaded HBM round trip (with one block of prefetch the first use of the
-    // vector was the top stall of the kernel, profiles/r01_ncu_dense_strip_smooth.txt).
     auto load_grid = [&](int yb, bool on, float2 (&dstg)[PX]) {
 #pragma unroll
       for (int r = 0; r < PX; ++r) {
         const int y = yb + ty + r * TROWS;
-        dstg[r] = (on && vx && y < H && !(dbg0 & 16)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
+        dstg[r] = (on && vx && (FULLV || y < H)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
       }
     };
     auto load_other = [&](int yb, bool on, float (&dsto)[PX][CR]) {
@@ -267,184 +306,227 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 #pragma unroll
       for (int r = 0; r < PX; ++r) {
         const int y = yb + ty + r * TROWS;
-        const bool live = on && vx && y < H;
+        const bool live = on && vx && (FULLV || y < H);
 #pragma unroll
         for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldg(point + (c * HWi + y * W + x)) : 0.f;
       }
     };
-    float2 g[PX], g1[PX];
-    float other[PX][CR];
-    load_grid(j0 * RB, true, g);
-    load_grid(j0 * RB + RB, nb > 1, g1);
-    load_other(j0 * RB, true, other);
-    // ring position of the window's top slot (slot load sb + jj): buffer b0, phase parity q0
+    // two alternating register sets: block jj uses set jj & 1.  Flow vectors of block jj+2 are loaded into the set of
+    // block jj as soon as its coordinates are computed; the pointwise operand of block jj+1 goes into the other set at
+    // the top of block jj (that set was consumed at the end of block jj-1).
+    float2 gbuf[2][PX];
+    float obuf[2][PX][CR];
+    load_grid(j0 * RB, true, gbuf[0]);
+    load_grid(j0 * RB + RB, nb > 1, gbuf[1]);
+    load_other(j0 * RB, true, obuf[0]);
+    // ring position of the window's top slot (slot load sb + jj): slot b0, phase parity q0
     int b0 = sb % NS;
     unsigned q0 = static_cast<unsigned>(sb / NS) & 1u;
 
-    for (int jj = 0; jj < nb; ++jj, ++kglob) {
-      const int y0 = (j0 + jj) * RB;
-      const int wy0 = y0 - HALO_Y;
-      const int pix0 = (y0 + ty) * W + x;
-
-      // ---- taps of this thread's PX pixels (registers only, branch-free)
-      BlockTaps<PX> T;
-      T.dxm = 0u; T.dym = 0u; T.valid = 0u;
-      unsigned outm = 0u;
+    for (int jj0 = 0; jj0 < nb; jj0 += 2) {
 #pragma unroll
-      for (int r = 0; r < PX; ++r) {
-        const int y = y0 + ty + r * TROWS;
-        const bool live = vx && (y < H);
-        const GsTap t = gs_setup<NM>(g[r].x, g[r].y, H, W, false);
-        T.wnw[r] = t.nw; T.wne[r] = t.ne; T.wsw[r] = t.sw; T.wse[r] = t.se;
-        const int lx = t.ix - xbase, d = t.iy - wy0;
-        // the taps that are accumulated must lie in the window: lx in [0, BOXW-1-dx], d in [0, WIN_ROWS-1-dy]
-        const bool in_box = (static_cast<unsigned>(lx) <= static_cast<unsigned>(BOXW - 1 - t.dx)) &&
-                            (static_cast<unsigned>(d) <= static_cast<unsigned>(WIN_ROWS - 1 - t.dy));
-        int sN = b0 + (d >> 3);
-        sN -= (sN >= NS) ? NS : 0;
-        int sS = b0 + ((d + 1) >> 3);
-        sS -= (sS >= NS) ? NS : 0;
-        const int aN = sN * slot_floats + (d & 7) * BOXW + lx;
-        const int aS = sS * slot_floats + ((d + 1) & 7) * BOXW + lx;
-        T.aN[r] = in_box ? aN : 0;
-        T.aS[r] = in_box ? aS : 0;
-        if (dbg0 & 4) { T.aN[r] = tid + r * BOXW; T.aS[r] = tid + (r + 1) * BOXW; T.wnw[r] = T.wne[r] = T.wsw[r] = T.wse[r] = 0.25f; }
-        if (live && !in_box) outm |= 1u << r;
-        if (live) T.valid |= 1u << r;
-        if (t.dx) T.dxm |= 1u << r;
-        if (t.dy) T.dym |= 1u << r;
-      }
-      // ---- prefetches for the following blocks (registers only; nothing here depends on the ring)
-      float2 g2[PX];
-      float other_next[PX][CR];
-      load_grid(y0 + 2 * RB, jj + 2 < nb, g2);
-      load_other(y0 + RB, jj + 1 < nb, other_next);
-      const bool use_global = __any_sync(0xffffffffu, outm != 0u);
+      for (int hb = 0; hb < 2; ++hb) {
+        const int jj = jj0 + hb;
+        if (jj >= nb) break;
+        float2 (&g)[PX] = gbuf[hb];
+        float (&other)[PX][CR] = obuf[hb];
+        const int y0 = (j0 + jj) * RB;
+        const int wy0 = y0 - HALO_Y;
+        const int pix0 = (y0 + ty) * W + x;
+        const int ky = -0x4B000000 - wy0;            // window row of a tap: mantissa bits of (iy + 2^23) + ky
+        const int rb0 = b0 * RB;                     // ring row of the window's top row
 
-      // ---- the ring slots of this block's window: the newest one, and all of them at the start of a segment
-#ifdef FUVS_STRIP_PROF
-      const long long prof_w0 = clock64();
-#endif
-      if (jj == 0) {
+        load_other(y0 + RB, jj + 1 < nb, obuf[hb ^ 1]);
+
+        // ---- coordinates, weights and ring addresses of this thread's two pixels (registers only, branch-free)
+        uint32_t aN[PX], aS[PX];
+        float wnw[PX], wne[PX], wsw[PX], wse[PX];
+        bool pdx[PX], pdy[PX], live[PX];
+        bool outside = false;
 #pragma unroll
-        for (int i = 0; i < WIN - 1; ++i) {
-          const int b = b0 + i;
+        for (int r = 0; r < PX; ++r) {
+          live[r] = FULLV || (vx && (y0 + ty + r * TROWS < H));
+          // gs_source_index<Nm>(.., align_corners=False) + clip_coordinates, as in fuvs_common.cuh
+          const float ix = fminf(Wm1, fmaxf(__fmul_rn(__fmaf_rn(__fadd_rn(g[r].x, 1.f), Wf, -1.f), 0.5f), 0.f));
+          const float iy = fminf(Hm1, fmaxf(__fmul_rn(__fmaf_rn(__fadd_rn(g[r].y, 1.f), Hf, -1.f), 0.5f), 0.f));
+          // floor and float->int without the conversion pipe: t = i + 2^23 rounded down carries floor(i) in its mantissa
+          const float tfx = __fadd_rd(ix, 8388608.f), tfy = __fadd_rd(iy, 8388608.f);
+          const float fx = __fsub_rn(tfx, 8388608.f), fy = __fsub_rn(tfy, 8388608.f);
+          const float ax = __fsub_rn(__fadd_rn(fx, 1.f), ix), bx = __fsub_rn(ix, fx);
+          const float ay = __fsub_rn(__fadd_rn(fy, 1.f), iy), by = __fsub_rn(iy, fy);
+          wnw[r] = __fmul_rn(ax, ay); wne[r] = __fmul_rn(bx, ay); wsw[r] = __fmul_rn(ax, by); wse[r] = __fmul_rn(bx, by);
+          pdx[r] = ix < Wm1;                         // the east neighbour exists  (ix_nw + 1 < W)
+          pdy[r] = iy < Hm1;                         // the south neighbour exists (iy_nw + 1 < H)
+          const unsigned lx = static_cast<unsigned>(__float_as_int(tfx) + kx);
+          const unsigned d = static_cast<unsigned>(__float_as_int(tfy) + ky);
+          // the 2x2 footprint inside the window: lx in [0, BOXW-2], d in [0, WIN_ROWS-2].  A tap clipped to the right
+          // image edge (no east neighbour) may sit in the window's last column: the east address then points at the
+          // next row / the pad behind the ring and its value is never accumulated.
+          const bool in_box = (lx <= static_cast<unsigned>(pdx[r] ? BOXW - 2 : BOXW - 1)) &&
+                              (d <= static_cast<unsigned>(WIN_ROWS - 2));
+          if (live[r] && !in_box) outside = true;
+          unsigned rr = d + static_cast<unsigned>(rb0);
+          rr = min(rr, rr - static_cast<unsigned>(NSR));            // wrap: rr - NSR is huge when rr < NSR
+          const uint32_t a = ring0 + (rr * BOXW + lx) * 4u;
+          aN[r] = in_box ? a : ring0;
+          aS[r] = in_box ? ((rr == static_cast<unsigned>(NSR - 1)) ? a - static_cast<uint32_t>((NSR - 1) * BOXW) * 4u
+                                                                    : a + BOXW * 4u)
+                         : ring0;
+        }
+        // ---- this set's flow vectors are consumed: refill it for block jj + 2 (nothing here depends on the ring)
+        load_grid(y0 + 2 * RB, jj + 2 < nb, g);
+        const bool use_global = __any_sync(0xffffffffu, outside);
+        refill_if_last();
+
+        // ---- the ring slots of this block's window: the newest one, and all of them at the start of a segment
+        if (jj == 0) {
+#pragma unroll
+          for (int i = 0; i < WIN - 1; ++i) {
+            const int b = b0 + i;
+            const bool wrap = b >= NS;
+            mbar_wait(bar0 + 8u * (wrap ? b - NS : b), q0 ^ (wrap ? 1u : 0u));
+          }
+        }
+        {
+          const int b = b0 + WIN - 1;
           const bool wrap = b >= NS;
           mbar_wait(bar0 + 8u * (wrap ? b - NS : b), q0 ^ (wrap ? 1u : 0u));
         }
-      }
-      {
-        const int b = b0 + WIN - 1;
-        const bool wrap = b >= NS;
-        mbar_wait(bar0 + 8u * (wrap ? b - NS : b), q0 ^ (wrap ? 1u : 0u));
-      }
 
-#ifdef FUVS_STRIP_PROF
-      if (kglob == 0) prof_first = clock64() - prof_w0; else prof_wait += clock64() - prof_w0;
-#endif
-      unsigned labs = 0u;                        // labels of this thread's pixels, 8 bits each
-      if (use_global) {
-        labs = block_from_global<NM, PX, TROWS>(&A, side, EMIT, do_key0, C, H, W, x, y0 + ty, T.valid);
-      } else {
-        ArgMax am[PX];
+        if (use_global) {
+          unsigned valid = 0u;
 #pragma unroll
-        for (int r = 0; r < PX; ++r) am[r].init(-INFINITY);   // push(v, 0) then always selects class 0 first
-        int sK = b0 + HALO_Y / RB;
-        sK -= (sK >= NS) ? NS : 0;
-        const int key_loc = sK * slot_floats + ty * BOXW + (min(x, W - 1) - xbase);
-        const bool w_dst = dst != nullptr && !(dbg0 & 2);
-        const bool w_lp = EMIT && logit_out != nullptr;
-        const bool w_l0 = KEY0 && A.logit0 != nullptr;
-        // One code path for interior and border pixels: ATen skips the taps whose neighbour is outside the image
-        // (within_bounds_2d), which is a predicated FFMA here — the tap value is loaded regardless (its address
-        // stays inside the ring) and simply not accumulated.  A separate predicated slow path made the CTAs of the
-        // edge strips, where border clipping is common, pace the whole launch.
+          for (int r = 0; r < PX; ++r) valid |= (live[r] ? 1u : 0u) << r;
+          block_from_global(&A, side, EMIT, do_key0, C, H, W, x, y0 + ty, valid);
+        } else {
+          const bool w_dst = WDST && dst != nullptr;
+          const bool w_lp = EMIT && logit_out != nullptr;
+          const bool w_l0 = KEY0 && A.logit0 != nullptr;
+          // own pixels inside the ring (frame 0 of step 1): window rows HALO_Y + ty + r*TROWS
+          uint32_t akey[PX];
+          if (KEY0) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          const float* pl = bufs + c * PLANE;
-          float v00[PX], v01[PX], v10[PX], v11[PX];
-#pragma unroll
-          for (int r = 0; r < PX; ++r) {
-            if (dbg0 & 1) { v00[r] = v01[r] = v10[r] = v11[r] = __int_as_float(T.aN[r] + c); continue; }
-            v00[r] = pl[T.aN[r]]; v01[r] = pl[T.aN[r] + 1];
-            v10[r] = pl[T.aS[r]]; v11[r] = pl[T.aS[r] + 1];
-          }
-#pragma unroll
-          for (int r = 0; r < PX; ++r) {
-            const bool live = FULLV || ((T.valid >> r) & 1u);
-            const bool dx = (T.dxm >> r) & 1u, dy = (T.dym >> r) & 1u;
-            const int gi = c * HWi + pix0 + r * rstride;
-            float acc = 0.f;
-            acc = tap_acc<NM>(acc, v00[r], T.wnw[r]);
-            if (dx) acc = tap_acc<NM>(acc, v01[r], T.wne[r]);
-            if (dy) acc = tap_acc<NM>(acc, v10[r], T.wsw[r]);
-            if (dx && dy) acc = tap_acc<NM>(acc, v11[r], T.wse[r]);
-            if (w_dst && live) dst[gi] = acc;
-            if (EMIT) {
-              const float o = CT > 0 ? other[r][CT > 0 ? c : 0] : (live ? __ldg(point + gi) : 0.f);
-              // fl(fl(w_this*acc) + fl(w_point*o)): IEEE addition is commutative, so one operand order serves both
-              // sides (the reference adds the forward term first on both) and the code is not duplicated per side
-              const float v = blend2(w_this, acc, w_point, o);
-              am[r].push(v, c);
-              if (w_lp && live) __stcs(logit_out + gi, v);
+            for (int r = 0; r < PX; ++r) {
+              unsigned rr = static_cast<unsigned>(rb0 + HALO_Y + ty + r * TROWS);
+              rr = min(rr, rr - static_cast<unsigned>(NSR));
+              akey[r] = colbase + rr * (BOXW * 4u);
             }
+          }
+          ArgMax am[PX];
+#pragma unroll
+          for (int r = 0; r < PX; ++r) am[r].init(-INFINITY);   // push(v, 0) then always selects class 0 first
+          if constexpr (CT > 0) {
+            constexpr int CHB = NSC * RB * BOXW * 4;             // bytes between channels of the ring
+            // ---- one burst: every tap of both pixels (4 CT loads each), then the key-frame values
+            float v[PX][CT][4];
+            float vk[PX][CT];
+            static_for<PX>([&](auto r_) {
+              constexpr int r = decltype(r_)::value;
+              static_for<CT>([&](auto c_) {
+                constexpr int c = decltype(c_)::value;
+                v[r][c][0] = lds_imm<c * CHB>(aN[r]);
+                v[r][c][1] = lds_imm<c * CHB + 4>(aN[r]);
+                v[r][c][2] = lds_imm<c * CHB>(aS[r]);
+                v[r][c][3] = lds_imm<c * CHB + 4>(aS[r]);
+              });
+            });
             if (KEY0 && do_key0) {
-              const float v = pl[key_loc + r * (TROWS * BOXW)];
-              am[r].push(v, c);
-              if (w_l0 && live) __stcs(A.logit0 + gi, v);
+              static_for<PX>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                static_for<CT>([&](auto c_) {
+                  constexpr int c = decltype(c_)::value;
+                  vk[r][c] = lds_imm<c * CHB>(akey[r]);
+                });
+              });
+            }
+            // ---- FMA chains in ATen's order (nw, ne, sw, se; neighbours outside the image are skipped), stores, blends
+#pragma unroll
+            for (int r = 0; r < PX; ++r) {
+              const bool dxy = pdx[r] && pdy[r];
+#pragma unroll
+              for (int c = 0; c < CT; ++c) {
+                const int gi = c * HWi + pix0 + r * rstride;
+                float acc = tap_acc<Nm>(0.f, v[r][c][0], wnw[r]);
+                if (pdx[r]) acc = tap_acc<Nm>(acc, v[r][c][1], wne[r]);
+                if (pdy[r]) acc = tap_acc<Nm>(acc, v[r][c][2], wsw[r]);
+                if (dxy) acc = tap_acc<Nm>(acc, v[r][c][3], wse[r]);
+                if (w_dst && live[r]) dst[gi] = acc;
+                if (EMIT) {
+                  // fl(fl(w_this*acc) + fl(w_point*o)): IEEE addition is commutative, so one operand order serves both
+                  // sides (the reference adds the forward term first on both) and the code is not duplicated per side
+                  const float val = blend2(w_this, acc, w_point, other[r][c]);
+                  am[r].push(val, c);
+                  if (w_lp && live[r]) __stcs(logit_out + gi, val);
+                }
+                if (KEY0 && do_key0) {
+                  am[r].push(vk[r][c], c);
+                  if (w_l0 && live[r]) __stcs(A.logit0 + gi, vk[r][c]);
+                }
+              }
+            }
+          } else {
+            const uint32_t chb = static_cast<uint32_t>(chan_floats) * 4u;
+#pragma unroll
+            for (int r = 0; r < PX; ++r) {
+              const bool dxy = pdx[r] && pdy[r];
+              for (int c = 0; c < C; ++c) {
+                const uint32_t co = static_cast<uint32_t>(c) * chb;
+                const float v00 = lds_rt(aN[r] + co), v01 = lds_rt(aN[r] + co + 4u);
+                const float v10 = lds_rt(aS[r] + co), v11 = lds_rt(aS[r] + co + 4u);
+                const int gi = c * HWi + pix0 + r * rstride;
+                float acc = tap_acc<Nm>(0.f, v00, wnw[r]);
+                if (pdx[r]) acc = tap_acc<Nm>(acc, v01, wne[r]);
+                if (pdy[r]) acc = tap_acc<Nm>(acc, v10, wsw[r]);
+                if (dxy) acc = tap_acc<Nm>(acc, v11, wse[r]);
+                if (w_dst && live[r]) dst[gi] = acc;
+                if (EMIT) {
+                  const float o = live[r] ? __ldg(point + gi) : 0.f;
+                  const float val = blend2(w_this, acc, w_point, o);
+                  am[r].push(val, c);
+                  if (w_lp && live[r]) __stcs(logit_out + gi, val);
+                }
+                if (KEY0 && do_key0) {
+                  const float val = lds_rt(akey[r] + co);
+                  am[r].push(val, c);
+                  if (w_l0 && live[r]) __stcs(A.logit0 + gi, val);
+                }
+              }
             }
           }
-        }
 #pragma unroll
-        for (int r = 0; r < PX; ++r) {
-          labs |= static_cast<unsigned>(am[r].idx) << (8 * r);
-          if (!((T.valid >> r) & 1u)) continue;
-          const int pix = pix0 + r * rstride;
-          if (EMIT && lab_out) lab_out[pix] = static_cast<uint8_t>(am[r].idx);
-          if (KEY0 && do_key0 && A.label0) A.label0[pix] = static_cast<uint8_t>(am[r].idx);
+          for (int r = 0; r < PX; ++r) {
+            if (!live[r]) continue;
+            const int pix = pix0 + r * rstride;
+            if (EMIT && lab_out) lab_out[pix] = static_cast<uint8_t>(am[r].idx);
+            if (KEY0 && do_key0 && A.label0) A.label0[pix] = static_cast<uint8_t>(am[r].idx);
+          }
         }
-      }
 
-      // ---- this warp is done with the ring for block kglob; the last warp to say so refills the dead buffers
-      const int rel_after = (jj < nb - 1) ? sb + jj + 1 : sb + nb + WIN - 1;
-      __syncwarp();
-      if (lane == 0) {
-        __threadfence_block();
-        if (atomicAdd(&done[kglob & 3], 1u) == NWARPS - 1) {
-          done[kglob & 3] = 0u;          // published to the other warps by the release-arrive inside issue()
-          for (int s = released + NS; s < rel_after + NS; ++s) issue(s);
-        }
+        // ---- this warp is done with the ring for block kglob (its gathers have returned: the FMAs consumed them).
+        // done[kglob & 3] only grows: visit v = kglob >> 2 of a counter is complete at (v + 1) * NWARPS; the skew
+        // between warps is bounded by the prefetch depth (< 4 blocks), so visits never mix.
+        __syncwarp();
+        tok_from = released;
+        tok_to = (jj < nb - 1) ? sb + jj + 1 : sb + nb + WIN - 1;
+        released = tok_to;
+        tok_want = (static_cast<unsigned>(kglob >> 2) + 1u) * NWARPS - 1u;
+        if (lane == 0) tok = atom_add_relaxed(done0 + 4u * (kglob & 3), 1u);
+        ++kglob;
+        if (++b0 == NS) { b0 = 0; q0 ^= 1u; }
       }
-      released = rel_after;
-
-#pragma unroll
-      for (int r = 0; r < PX; ++r) {
-        g[r] = g1[r];
-        g1[r] = g2[r];
-#pragma unroll
-        for (int c = 0; c < CR; ++c) other[r][c] = other_next[r][c];
-      }
-      if (++b0 == NS) { b0 = 0; q0 ^= 1u; }
     }
     sb += nb + WIN - 1;
-    kb += nb;
+    left -= nb;
+    ++u;
+    j0 = 0;
   }
-#ifdef FUVS_STRIP_PROF
-  if (tid == 0 && blockIdx.x < 148) {
-    unsigned long long* o = g_strip_prof + (prof_launch * 148 + blockIdx.x) * 4;
-    o[0] = clock64() - prof_t0;
-    o[1] = prof_wait;
-    o[2] = prof_first;
-    o[3] = B1 - B0;
-    if (blockIdx.x == 0) atomicAdd(&g_strip_launch, 1u);
-  }
-#endif
+  refill_if_last();                                // nothing left to load for this CTA: issue() ignores indices past the end
 }
 
-template <int CT, int NSC, int TROWS, bool EMIT, bool KEY0>
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV>
 int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   static SmemOptIn optin;
-  auto kern = dense_strip_kernel<Nm, CT, NSC, TROWS, EMIT, KEY0>;
+  auto kern = dense_strip_kernel<CT, NSC, EMIT, KEY0, WDST, FULLV>;
   const size_t smem = static_cast<size_t>(nslot) * C * PLANE * 4 + 256;
   if (!optin.ensure(kern, SMEM_LIMIT)) return 1;
   StripGeom g;
@@ -452,43 +534,45 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.nby = (H + RB - 1) / RB;
   g.total = 2 * g.nsx * g.nby;
   g.nslot = nslot;
-  static const int wkey0 = []() { const char* e = getenv("FUVS_STRIP_WKEY0"); return e ? atoi(e) : 9; }();
-  g.wl = KEY0 ? wkey0 : 8;                     // measured (eighths): 8 -> 244.6, 9 -> 242.7, 10 -> 245.3, 11 -> 247.6 us per interval
+  g.wl = KEY0 ? 9 : 8;                         // measured in r01 (eighths): 8 -> 244.6, 9 -> 242.7, 10 -> 245.3 us per interval
   g.wr = 8;
-  static const int wedge = []() { const char* e = getenv("FUVS_STRIP_WEDGE"); return e ? atoi(e) : 18; }();   // sixteenths
-  g.wedge = wedge;
-  static const int wstart = []() { const char* e = getenv("FUVS_STRIP_WSTART"); return e ? atoi(e) : 16; }();   // measured: 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
-  g.wstart = wstart < 0 ? 0 : wstart;
+  g.wedge = 18;                                // sixteenths
+  g.wstart = 16;                               // measured in r01: 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
-  static const bool pdl = []() { const char* e = getenv("FUVS_STRIP_PDL"); return !(e && e[0] == '0'); }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TW * TROWS);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  if (cudaLaunchKernelEx(&cfg, kern, maps, a, C, H, W, g) != cudaSuccess) return check_launch("fuvs_dense_interval(strip step)");
-  return check_launch("fuvs_dense_interval(strip step)");
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, a, C, H, W, g);
+  if (e != cudaSuccess) return set_error(FUVS_ECUDA, "fuvs_dense_interval(strip step): %s", cudaGetErrorString(e));
+  count_launch();
+  return FUVS_OK;
 }
 
-template <int CT, int NSC, int TROWS>
+template <int CT, int NSC, bool FULLV>
 int launch_ct(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
-  if (a.emitA) return launch_variant<CT, NSC, TROWS, true, false>(maps, a, C, H, W, nslot, st);
-  if (a.key0) return launch_variant<CT, NSC, TROWS, false, true>(maps, a, C, H, W, nslot, st);
-  return launch_variant<CT, NSC, TROWS, false, false>(maps, a, C, H, W, nslot, st);
+  const bool wdst = a.dstL != nullptr;
+  if (a.emitA) {
+    return wdst ? launch_variant<CT, NSC, true, false, true, FULLV>(maps, a, C, H, W, nslot, st)
+                : launch_variant<CT, NSC, true, false, false, FULLV>(maps, a, C, H, W, nslot, st);
+  }
+  if (a.key0) return launch_variant<CT, NSC, false, true, true, FULLV>(maps, a, C, H, W, nslot, st);
+  return launch_variant<CT, NSC, false, false, true, FULLV>(maps, a, C, H, W, nslot, st);
 }
 
-template <int TROWS>
-int launch_rows(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
+template <bool FULLV>
+int launch_full(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   switch (C) {
-    case 2: return launch_ct<2, NSLOT_C2, TROWS>(maps, a, C, H, W, nslot, st);
-    case 5: return launch_ct<5, NSLOT_C5, TROWS>(maps, a, C, H, W, nslot, st);
-    default: return launch_ct<0, 0, TROWS>(maps, a, C, H, W, nslot, st);
+    case 2: return launch_ct<2, NSLOT_C2, FULLV>(maps, a, C, H, W, nslot, st);
+    case 5: return launch_ct<5, NSLOT_C5, FULLV>(maps, a, C, H, W, nslot, st);
+    default: return launch_ct<0, 0, FULLV>(maps, a, C, H, W, nslot, st);
   }
 }
 
@@ -499,33 +583,17 @@ int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_
   if ((W & 3) != 0 || W < 4 || !aligned16(a.srcL) || !aligned16(a.srcR) || H >= 32768 || W >= 32768) return 1;
   if ((a.emitA && !a.pointR) || (a.emitB && !a.pointL) || (a.emitA != a.emitB)) return 1;
   if (a.key0 && (a.key0 != a.srcL || a.emitA)) return 1;
+  if ((a.dstL != nullptr) != (a.dstR != nullptr)) return 1;
+  if (!a.emitA && !a.dstL) return 1;             // a step that neither writes states nor emits frames does not exist
   if (!aligned8(a.gridL) || !aligned8(a.gridR)) return 1;
   if (C > 16 || static_cast<long long>(C) * H * W >= (1ll << 31)) return 1;
   const int nslot = nslot_for(C);
   if (nslot < WIN + 1) return 1;                 // the window of all channels does not fit: per-plane kernel
   StripMaps maps;
-  if (!make_map_chw(&maps.srcL, a.srcL, C, H, W, BOXW, RB, C) || !make_map_chw(&maps.srcR, a.srcR, C, H, W, BOXW, RB, C))
+  if (!make_map_chw(&maps.srcL, a.srcL, C, H, W, BOXW, RB, 1) || !make_map_chw(&maps.srcR, a.srcR, C, H, W, BOXW, RB, 1))
     return 1;
-#ifdef FUVS_STRIP_PROF
-  {
-    const char* e = getenv("FUVS_STRIP_DBG");
-    const int v = e ? atoi(e) : 0;
-    cudaMemcpyToSymbolAsync(g_strip_dbg, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
-  }
-#endif
-  static const int trows = []() {
-    const char* e = getenv("FUVS_STRIP_TROWS");
-    return (e && e[0] == '8') ? 8 : (e && e[0] == '2') ? 2 : 4;
-  }();
-  if (trows == 2) return launch_rows<2>(maps, a, C, H, W, nslot, st);
-  if (trows == 8) return launch_rows<8>(maps, a, C, H, W, nslot, st);
-  return launch_rows<4>(maps, a, C, H, W, nslot, st);
+  if ((W % TW) == 0 && (H % RB) == 0) return launch_full<true>(maps, a, C, H, W, nslot, st);
+  return launch_full<false>(maps, a, C, H, W, nslot, st);
 }
-
-#ifdef FUVS_STRIP_PROF
-extern "C" __attribute__((visibility("default"))) int fuvs_debug_strip_prof(unsigned long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, g_strip_prof, sizeof(g_strip_prof)) == cudaSuccess ? 0 : -1;
-}
-#endif
 
 }  // namespace fuvs
