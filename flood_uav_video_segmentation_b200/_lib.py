@@ -14,9 +14,9 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("FUVS_LIB_PATH") or os.path.join(_HERE, "lib", "libfuvs.so")   # override: developer A/B builds (build.py)
+LIB_PATH = os.path.join(_HERE, "lib", "libfuvs.so")
 
-FUVS_ABI_VERSION = 1
+FUVS_ABI_VERSION = 2
 FUVS_BINS_HISTC = 0
 FUVS_BINS_NPHIST = 1
 FUVS_MUTATE_PRED = 2
@@ -39,11 +39,16 @@ SIGNATURES = {
     "fuvs_warp_step": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fuvs_dense_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_dense_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_dense_interval_ptrs": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_block_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_block_interval_ptrs": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_block_clip": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_feature_scratch_floats": (_ll, [_i, _i, _i, _i, _i, _i]),
     "fuvs_feature_interval": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "fuvs_feature_interval_ptrs": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fuvs_upsample_bilinear_ac": (_i, [_p, _p, _ll, _i, _i, _i, _i, _p]),
+    "fuvs_upsample_argmax": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "fuvs_blend_argmax": (_i, [_p, _p, _d, _d, _i, _i, _ll, _p, _p, _p]),
     "fuvs_argmax": (_i, [_p, _i, _i, _ll, _p, _p, _p]),
     "fuvs_confusion": (_i, [_p, _i, _p, _i, _ll, _i, _i, _i, _p, _p]),
@@ -63,6 +68,25 @@ _lib = None
 
 class FuvsError(RuntimeError):
     """A libfuvs entry point returned a negative code."""
+
+
+def use_library(path: str) -> None:
+    """Developer hook (tools/ only): load another build of the library (build.py FUVS_BUILD_TAG) instead of the shipped
+    one.  Must be called before the first op; the product never calls it and no environment variable selects a library."""
+    global LIB_PATH, _lib
+    if _lib is not None:
+        raise FuvsError("use_library() must be called before the library is loaded")
+    LIB_PATH = path
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (const float* const*) for the *_ptrs / *_clip entries; None -> NULL."""
+    if tensors is None:
+        return None
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
 
 
 def load() -> C.CDLL:

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 # developer A/B builds: FUVS_BUILD_TAG=x FUVS_BUILD_DEFINES="-DFOO -DBAR" writes lib/libfuvs_x.so (objects in build_x/);
-# FUVS_LIB_PATH selects which library _lib.py loads.  The shipped library is always the untagged default build.
+# a tool selects it with _lib.use_library(path).  The shipped library is always the untagged default build.
 _TAG = os.environ.get("FUVS_BUILD_TAG", "")
 if _TAG:
     LIB = os.path.join(LIBDIR, f"libfuvs_{_TAG}.so")

@@ -83,8 +83,7 @@ static int launch_upsample(const float* src, float* dst, long long planes, int H
                            cudaStream_t st) {
   const long long out_plane = static_cast<long long>(Hout) * Wout;
   const int threads = 256;
-  static const bool v4 = []() { const char* e = getenv("FUVS_UPSAMPLE_V4"); return !(e && e[0] == '0'); }();   // A/B switch
-  if (v4 && (Wout & 3) == 0 && aligned16(dst) && out_plane < (1ll << 31)) {
+  if ((Wout & 3) == 0 && aligned16(dst) && out_plane < (1ll << 31)) {
     const long long items = out_plane >> 2;
     // few planes per thread column (grid.y), so that small plane counts still fill the SMs
     const long long bx4 = (items + threads - 1) / threads;
@@ -105,34 +104,36 @@ static int launch_upsample(const float* src, float* dst, long long planes, int H
 }
 
 // ---------------------------------------------------------------------------
-// block-grid chain step (both sides, low resolution)
+// block-grid chain step (low resolution): one launch advances both chains of up to CHAIN_MAX_IV intervals by one step
+// (blockIdx.z = 2 * interval + side).  A clip's intervals are independent until their label maps meet in the
+// temporal counts, so fuvs_block_clip pays the n-1 dependent launch latencies once per clip instead of per interval.
 // ---------------------------------------------------------------------------
+constexpr int CHAIN_MAX_IV = 8;
+struct ChainStepBatch {
+  const float* src[2 * CHAIN_MAX_IV];
+  const float* grid[2 * CHAIN_MAX_IV];
+  float* dst[2 * CHAIN_MAX_IV];
+};
+
+template <class NM>
+__device__ __forceinline__ void gs_fetch_all_cg(const float* src, long long in_plane, const GsTap& t, int Win, int C,
+                                                float* dst, int out_plane);
+
 template <class NM>
 __global__ void __launch_bounds__(256)
-block_chain_step_kernel(const float* __restrict__ srcL, const float* __restrict__ srcR,
-                        const float* __restrict__ gridL, const float* __restrict__ gridR,
-                        float* __restrict__ dstL, float* __restrict__ dstR, int C, int Hin, int Win, int Hg, int Wg,
-                        int early) {
-  // programmatic dependent launch: scheduled while the previous step drains.  `early` (steps 2..n-1: the predecessor
-  // is our own previous step, which never writes flow vectors and has itself waited for everything before it): the
-  // flow vector and the coordinate arithmetic do not wait for it, only the taps do.
+block_chain_step_kernel(const __grid_constant__ ChainStepBatch B, int C, int Hin, int Win, int Hg, int Wg) {
+  // programmatic dependent launch (when the launch carries the attribute): nothing is read before the wait — the flow
+  // vectors of a later interval may be written by a kernel that is still running
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   if (x >= Wg || y >= Hg) return;
-  const bool right = blockIdx.z != 0;
-  const float* src = right ? srcR : srcL;
-  const float* grid = right ? gridR : gridL;
-  float* dst = right ? dstR : dstL;
+  const int z = blockIdx.z;
   const int opix = y * Wg + x;
-  const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + opix);
+  const float2 g = __ldg(reinterpret_cast<const float2*>(B.grid[z]) + opix);
   const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, false);
-  if (early) asm volatile("griddepcontrol.wait;" ::: "memory");
-  const long long in_plane = static_cast<long long>(Hin) * Win;
-  const int out_plane = Hg * Wg;
-#pragma unroll 5
-  for (int c = 0; c < C; ++c) dst[c * out_plane + opix] = gs_fetch<NM>(src + c * in_plane, t, Win);
+  gs_fetch_all_cg<NM>(B.src[z], static_cast<long long>(Hin) * Win, t, Win, C, B.dst[z] + opix, Hg * Wg);
 }
 
 // ---------------------------------------------------------------------------
@@ -196,27 +197,6 @@ block_stream_kernel(const float* __restrict__ key0, const float* __restrict__ Ls
   }
 }
 
-// ---------------------------------------------------------------------------
-// Whole low-resolution chain in ONE launch: a thread-block cluster per side (8 CTAs x 1024 threads cover the 8 040
-// grid points of a 67x120 grid with one point per thread), cluster.sync() between the n-1 dependent steps instead
-// of n-1 kernel launches.  cluster.sync() is a release/acquire barrier at cluster scope (and invalidates L1), so the
-// states written in step j are visible to every CTA of the cluster in step j+1; they are read with ld.global.cg.
-// ---------------------------------------------------------------------------
-constexpr int CHAIN_CLUSTER = 8;
-constexpr int CHAIN_THREADS = 1024;
-
-template <class NM>
-__device__ __forceinline__ float gs_fetch_cg(const float* plane, const GsTap& t, int Win) {
-  const float* p = plane + t.off00;
-  const float v00 = __ldcg(p), v01 = __ldcg(p + t.dx), v10 = __ldcg(p + t.dy * Win), v11 = __ldcg(p + t.dy * Win + t.dx);
-  float acc = 0.f;
-  acc = tap_acc<NM>(acc, v00, t.nw);
-  if (t.dx) acc = tap_acc<NM>(acc, v01, t.ne);
-  if (t.dy) acc = tap_acc<NM>(acc, v10, t.sw);
-  if (t.dx & t.dy) acc = tap_acc<NM>(acc, v11, t.se);
-  return acc;
-}
-
 // All C channels of one grid point: the tap loads of up to 8 channels are issued before the first store.  Written as
 // `dst[c] = gs_fetch_cg(src + c)` the store of channel c — which may alias the source for all the compiler knows (both
 // live in the chain scratch) — keeps the loads of channel c+1 behind it in program order: C dependent L2 round
@@ -250,43 +230,19 @@ __device__ __forceinline__ void gs_fetch_all_cg(const float* src, long long in_p
   }
 }
 
-template <class NM>
-__global__ void __cluster_dims__(CHAIN_CLUSTER, 1, 1) __launch_bounds__(CHAIN_THREADS)
-block_chain_cluster_kernel(const float* __restrict__ prev, const float* __restrict__ next,
-                           const float* __restrict__ grids_left, const float* __restrict__ grids_right,
-                           float* Lst, float* Rst, int C, int H, int W, int Hg, int Wg, int n) {
-  const int side = blockIdx.x / CHAIN_CLUSTER;
-  const int crank = blockIdx.x - side * CHAIN_CLUSTER;
-  const float* key = side ? next : prev;
-  const float* grids = side ? grids_right : grids_left;
-  float* st = side ? Rst : Lst;
-  const int npts = Hg * Wg;
-  const long long ls = static_cast<long long>(C) * npts;
-  for (int j = 1; j <= n - 1; ++j) {
-    const float* src = (j == 1) ? key : st + (j - 2) * ls;
-    const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
-    const long long in_plane = static_cast<long long>(Hin) * Win;
-    const float* grid = grids + static_cast<long long>(j - 1) * npts * 2;
-    float* dst = st + (j - 1) * ls;
-    for (int pt = crank * CHAIN_THREADS + threadIdx.x; pt < npts; pt += CHAIN_CLUSTER * CHAIN_THREADS) {
-      const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
-      const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, false);
-      gs_fetch_all_cg<NM>(src, in_plane, t, Win, C, dst + pt, npts);
-    }
-    if (j < n - 1) {
-      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
-  }
-}
+// Whole chain of ONE interval as a cooperative launch over the GPU: one thread per (side, grid point), grid.sync()
+// between the dependent steps (eager launches: each extra launch costs the host ~3 us).  Spreading the 2 x 8 040
+// points over ~63 CTAs keeps the scattered tap loads off a handful of L1s.
+struct ChainGrids {
+  const float* left[FUVS_MAX_FRAMES];
+  const float* right[FUVS_MAX_FRAMES];
+};
 
-// Same chain as a cooperative launch over the whole GPU: one thread per (side, grid point), grid.sync() between the
-// dependent steps.  Spreading the 2 x 8 040 points over ~63 CTAs keeps the scattered tap loads off a handful of L1s
-// (the 16-CTA cluster version is L1-throughput bound at 34 us; n-1 separate launches cost ~6 us each).
 template <class NM>
 __global__ void __launch_bounds__(256)
 block_chain_coop_kernel(const float* __restrict__ prev, const float* __restrict__ next,
-                        const float* __restrict__ grids_left, const float* __restrict__ grids_right,
-                        float* Lst, float* Rst, int C, int H, int W, int Hg, int Wg, int n) {
+                        const __grid_constant__ ChainGrids G, float* Lst, float* Rst, int C, int H, int W, int Hg,
+                        int Wg, int n) {
   namespace cg = cooperative_groups;
   cg::grid_group gridg = cg::this_grid();
   const int npts = Hg * Wg;
@@ -301,7 +257,7 @@ block_chain_coop_kernel(const float* __restrict__ prev, const float* __restrict_
       const float* src = (j == 1) ? (side ? next : prev) : st + (j - 2) * ls;
       const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
       const long long in_plane = static_cast<long long>(Hin) * Win;
-      const float* grid = (side ? grids_right : grids_left) + static_cast<long long>(j - 1) * npts * 2;
+      const float* grid = side ? G.right[j - 1] : G.left[j - 1];
       float* dst = st + (j - 1) * ls;
       const float2 g = __ldg(reinterpret_cast<const float2*>(grid) + pt);
       const GsTap tp = gs_setup<NM>(g.x, g.y, Hin, Win, false);
@@ -477,126 +433,43 @@ extern "C" long long fuvs_block_scratch_floats(int C, int Hg, int Wg, int n) {
   return 2ll * (n - 1) * C * static_cast<long long>(Hg) * Wg;
 }
 
-extern "C" int fuvs_block_interval(const float* prev, const float* next, const float* grids_left,
-                                   const float* grids_right, int C, int H, int W, int Hg, int Wg, int n,
-                                   float* scratch, uint8_t* labels, float* logits, const uint8_t* tc_prev,
-                                   long long* counts, int ignore_index, fuvs_stream_t stream) {
-  using namespace fuvs;
-  if (int e = device_ok()) return e;
-  if (!prev || C < 1 || H < 1 || W < 1 || n < 1) return set_error(FUVS_EINVAL, "block: bad shape C=%d H=%d W=%d n=%d", C, H, W, n);
-  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "block: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
-  if (n > 1 && (!next || !grids_left || !grids_right || !scratch || Hg < 1 || Wg < 1))
-    return set_error(FUVS_EINVAL, "block: next/grids/scratch are NULL or grid is empty (Hg=%d Wg=%d) but n=%d", Hg, Wg, n);
-  if ((labels || counts) && C > 256) return set_error(FUVS_EINVAL, "block: uint8 label maps need C <= 256 (C=%d)", C);
-  if (counts && !labels) return set_error(FUVS_EINVAL, "block: counts need the label maps (labels is NULL)");
-  const long long HW = static_cast<long long>(H) * W;
-  if (HW >= (1ll << 31) || static_cast<long long>(C) * Hg * Wg * 2 * n >= (1ll << 31))
-    return set_error(FUVS_EINVAL, "block: problem exceeds 32-bit indexing");
-  if (n > 1 && (!aligned8(grids_left) || !aligned8(grids_right))) return set_error(FUVS_EALIGN, "block: grids must be 8-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long S = static_cast<long long>(C) * HW;
+namespace fuvs {
 
-  if (n == 1) {
-    if (labels) {
-      if (int e = launch_argmax(prev, 1, C, HW, labels, nullptr, st)) return e;
+// Frames of one interval from its finished chain states: up-sample + blend + arg-max (+ counts when the row kernel
+// takes the shape; otherwise the caller runs fuvs_temporal_counts).  Returns 0 / negative; *counts_done says whether
+// the temporal counts were fused.
+static int block_frames(const float* prev, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
+                        int n, uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, cudaStream_t st, bool* counts_done) {
+  *counts_done = false;
+  if (!labels && !logits) return FUVS_OK;
+  BlendWeights w;
+  make_blend_weights(n, &w);
+  const float sh = ac_scale(Hg, H), sw = ac_scale(Wg, W);
+  if (Hg == H && Wg == W) {
+    // sizes already match: the reference skips the interpolate call (flow/model.py:217), per-pixel kernel
+    dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
+    if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
+    switch (C) {
+      case 2: block_stream_kernel<Nm, 2><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+      case 5: block_stream_kernel<Nm, 5><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
+      default: block_stream_kernel<Nm, 0><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
     }
-    if (logits) {
-      if (cudaMemcpyAsync(logits, prev, S * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
-        return set_error(FUVS_ECUDA, "block: logits copy failed");
-    }
-  } else {
-    const long long ls = static_cast<long long>(C) * Hg * Wg;
-    float* Lst = scratch;                    // L_1 .. L_{n-1}
-    float* Rst = scratch + (n - 1) * ls;     // R_1 .. R_{n-1}
-    // FUVS_BLOCK_CHAIN = coop (one cooperative launch, grid.sync between steps) | cluster (one launch, one 8-CTA
-    // cluster per side) | steps (n-1 launches).  Default: steps while the stream is being captured into a CUDA graph
-    // (kernel-to-kernel latency inside a graph is below a grid-wide barrier: 62.7 vs 65.8 us per 1080p interval),
-    // coop for eager launches (each extra launch costs the host ~3 us: 67.8 vs 70.4 us).
-    static const int chain_env = []() {
-      const char* e = getenv("FUVS_BLOCK_CHAIN");
-      return !e ? -1 : (e[0] == 's') ? 2 : (e[0] == 'c' && e[1] == 'l') ? 1 : 0;
-    }();
-    int chain_mode = chain_env;
-    if (chain_mode < 0) {
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-      chain_mode = (cap == cudaStreamCaptureStatusActive) ? 2 : 0;
-    }
-    bool done = false;
-    if (chain_mode == 0) {
-      const int total = 2 * Hg * Wg;
-      int cgrid = (total + 255) / 256;
-      static int bps = blocks_per_sm(block_chain_coop_kernel<Nm>, 256);
-      const int cap = sm_count() * bps;
-      if (cgrid > cap) cgrid = cap;
-      void* args[] = {(void*)&prev, (void*)&next, (void*)&grids_left, (void*)&grids_right, (void*)&Lst, (void*)&Rst,
-                      (void*)&C, (void*)&H, (void*)&W, (void*)&Hg, (void*)&Wg, (void*)&n};
-      if (cudaLaunchCooperativeKernel((const void*)block_chain_coop_kernel<Nm>, dim3(cgrid), dim3(256), args, 0, st) ==
-          cudaSuccess) {
-        if (int e = check_launch("fuvs_block_interval(chain coop)")) return e;
-        done = true;
-      } else {
-        cudaGetLastError();   // cooperative launch unavailable: per-step launches below
-      }
-    }
-    if (done) {
-    } else if (chain_mode == 1) {
-      block_chain_cluster_kernel<Nm><<<2 * CHAIN_CLUSTER, CHAIN_THREADS, 0, st>>>(prev, next, grids_left, grids_right,
-                                                                                  Lst, Rst, C, H, W, Hg, Wg, n);
-      if (int e = check_launch("fuvs_block_interval(chain cluster)")) return e;
-    } else {
-      dim3 cgrid((Wg + 31) / 32, (Hg + 7) / 8, 2), cblock(32, 8);
-      for (int j = 1; j <= n - 1; ++j) {
-        const float* sL = (j == 1) ? prev : Lst + (j - 2) * ls;
-        const float* sR = (j == 1) ? next : Rst + (j - 2) * ls;
-        const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = cgrid;
-        cfg.blockDim = cblock;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        // measured: with the attribute the 1080p interval takes 97 us instead of 63 us (the early-launched CTAs of the
-        // later steps and of the stream kernel sit on the SMs the running step needs); it only pays at crop size
-        static const bool step_pdl = []() { const char* e = getenv("FUVS_BLOCK_CHAIN_PDL"); return e && e[0] == '1'; }();
-        cfg.numAttrs = step_pdl ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, block_chain_step_kernel<Nm>, sL, sR,
-                           grids_left + static_cast<long long>(j - 1) * Hg * Wg * 2,
-                           grids_right + static_cast<long long>(j - 1) * Hg * Wg * 2, Lst + (j - 1) * ls,
-                           Rst + (j - 1) * ls, C, Hin, Win, Hg, Wg, j >= 2 ? 1 : 0);
-        if (int e = check_launch("fuvs_block_interval(chain)")) return e;
-      }
-    }
-    if (labels || logits) {
-      BlendWeights w;
-      make_blend_weights(n, &w);
-      const float sh = ac_scale(Hg, H), sw = ac_scale(Wg, W);
-      if (Hg == H && Wg == W) {
-        // sizes already match: the reference skips the interpolate call (flow/model.py:217), per-pixel kernel
-        dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
-        if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
-        switch (C) {
-          case 2: block_stream_kernel<Nm, 2><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
-          case 5: block_stream_kernel<Nm, 5><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
-          default: block_stream_kernel<Nm, 0><<<grid, block, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, w); break;
-        }
-        if (int e = check_launch("fuvs_block_interval(stream)")) return e;
-      } else {
-        // FUVS_BLOCK_STREAM=cols forces the column-strip kernel (A/B measurements); default: source-row intervals
-        static const bool want_rows = []() { const char* e = getenv("FUVS_BLOCK_STREAM"); return !(e && e[0] == 'c'); }();
-        if (want_rows) {
-          const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev,
-                                                 counts, ignore_index, w, st);
-          if (r < 0) return r;
-          if (r == 0) return FUVS_OK;
-        }
-        dim3 grid((W + STHREADS - 1) / STHREADS, (H + SROWS - 1) / SROWS);
-        if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
-        auto cu = reinterpret_cast<unsigned long long*>(counts);
-        // counts are fused when the class count has a field-packed counter and ignore_index cannot collide with a class
-        const bool fuse = counts && labels && C <= 5 && (ignore_index < 0 || ignore_index >= C) && n * SROWS <= 4096;
+    return check_launch("fuvs_block_interval(stream)");
+  }
+  // source-row intervals (block_rows.cu) for the shapes it takes (2 <= C <= 5, W % 4 == 0), column strips otherwise
+  const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts,
+                                         ignore_index, w, st);
+  if (r < 0) return r;
+  if (r == 0) {
+    *counts_done = counts != nullptr;
+    return FUVS_OK;
+  }
+  dim3 grid((W + STHREADS - 1) / STHREADS, (H + SROWS - 1) / SROWS);
+  if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
+  auto cu = reinterpret_cast<unsigned long long*>(counts);
+  // counts are fused when the class count has a field-packed counter and ignore_index cannot collide with a class
+  const bool fuse = counts && labels && C <= 5 && (ignore_index < 0 || ignore_index >= C) && n * SROWS <= 4096;
 #define FUVS_COLS2(CT_, CNT_, LG_, FR_)                                                                               \
   block_stream_cols_kernel<Nm, CT_, CNT_, LG_, FR_><<<grid, STHREADS, 0, st>>>(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, \
                                                                                labels, logits, tc_prev, cu, ignore_index, w)
@@ -606,24 +479,179 @@ extern "C" int fuvs_block_interval(const float* prev, const float* next, const f
     else if (H % SROWS == 0) FUVS_COLS2(CT_, CNT_, false, true);        \
     else FUVS_COLS2(CT_, CNT_, false, false);                           \
   } while (0)
-        if (fuse) {
-          switch (C) {
-            case 1: FUVS_COLS(1, true); break;
-            case 2: FUVS_COLS(2, true); break;
-            case 3: FUVS_COLS(3, true); break;
-            case 4: FUVS_COLS(4, true); break;
-            default: FUVS_COLS(5, true); break;
-          }
-        } else {
-          FUVS_COLS(0, false);
-        }
+  if (fuse) {
+    switch (C) {
+      case 1: FUVS_COLS(1, true); break;
+      case 2: FUVS_COLS(2, true); break;
+      case 3: FUVS_COLS(3, true); break;
+      case 4: FUVS_COLS(4, true); break;
+      default: FUVS_COLS(5, true); break;
+    }
+  } else {
+    FUVS_COLS(0, false);
+  }
 #undef FUVS_COLS
 #undef FUVS_COLS2
-        if (int e = check_launch("fuvs_block_interval(stream cols)")) return e;
-        if (fuse) return FUVS_OK;
+  if (int e = check_launch("fuvs_block_interval(stream cols)")) return e;
+  *counts_done = fuse;
+  return FUVS_OK;
+}
+
+// m consecutive intervals of one clip: keys[i], keys[i+1] bracket interval i; gl / gr hold m * (n-1) grid pointers.
+static int block_clip_impl(int m, const float* const* keys, const float* const* gl, const float* const* gr, int C,
+                           int H, int W, int Hg, int Wg, int n, float* scratch, uint8_t* const* labels,
+                           float* const* logits, const uint8_t* tc_prev, long long* counts, int ignore_index,
+                           cudaStream_t st, const char* who) {
+  if (int e = device_ok()) return e;
+  if (m < 1 || !keys || C < 1 || H < 1 || W < 1 || n < 1)
+    return set_error(FUVS_EINVAL, "%s: bad shape m=%d C=%d H=%d W=%d n=%d", who, m, C, H, W, n);
+  if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "%s: n=%d exceeds %d frames per interval", who, n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!gl || !gr || !scratch || Hg < 1 || Wg < 1))
+    return set_error(FUVS_EINVAL, "%s: grids/scratch are NULL or grid is empty (Hg=%d Wg=%d) but n=%d", who, Hg, Wg, n);
+  const bool want_labels = labels != nullptr && labels[0] != nullptr;
+  const bool want_logits = logits != nullptr && logits[0] != nullptr;
+  if ((want_labels || counts) && C > 256) return set_error(FUVS_EINVAL, "%s: uint8 label maps need C <= 256 (C=%d)", who, C);
+  if (counts && !want_labels) return set_error(FUVS_EINVAL, "%s: counts need the label maps (labels is NULL)", who);
+  const long long HW = static_cast<long long>(H) * W;
+  if (HW >= (1ll << 31) || static_cast<long long>(C) * Hg * Wg * 2 * n >= (1ll << 31))
+    return set_error(FUVS_EINVAL, "%s: problem exceeds 32-bit indexing", who);
+  for (int i = 0; i <= (n > 1 ? m : m - 1); ++i)
+    if (!keys[i]) return set_error(FUVS_EINVAL, "%s: key frame %d is NULL", who, i);
+  for (int i = 0; i < m; ++i) {
+    if ((want_labels && !labels[i]) || (want_logits && !logits[i]))
+      return set_error(FUVS_EINVAL, "%s: output pointer of interval %d is NULL", who, i);
+  }
+  for (int i = 0; n > 1 && i < m * (n - 1); ++i) {
+    if (!gl[i] || !gr[i]) return set_error(FUVS_EINVAL, "%s: grid %d is NULL", who, i);
+    if (!aligned8(gl[i]) || !aligned8(gr[i])) return set_error(FUVS_EALIGN, "%s: grids must be 8-byte aligned", who);
+  }
+  const long long S = static_cast<long long>(C) * HW;
+  const long long ls = static_cast<long long>(C) * Hg * Wg;          // one low-resolution state
+  const long long per_iv = 2ll * (n - 1) * ls;                       // scratch of one interval: L_1..L_{n-1}, R_1..R_{n-1}
+
+  if (n == 1) {
+    for (int i = 0; i < m; ++i) {
+      if (want_labels) {
+        if (int e = launch_argmax(keys[i], 1, C, HW, labels[i], nullptr, st)) return e;
+      }
+      if (want_logits) {
+        if (cudaMemcpyAsync(logits[i], keys[i], S * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+          return set_error(FUVS_ECUDA, "%s: logits copy failed", who);
+      }
+      if (counts) {
+        const uint8_t* tp = (i == 0) ? tc_prev : labels[i - 1];
+        if (int e = launch_temporal_counts(labels[i], 1, HW, tp, C, ignore_index, counts, st)) return e;
+      }
+    }
+    return FUVS_OK;
+  }
+
+  // ---- chains.  One interval, eager launch: one cooperative launch with grid.sync between the steps.  While the
+  // stream is being captured (kernel-to-kernel latency inside a graph is below a grid-wide barrier: 62.7 vs 65.8 us
+  // per 1080p interval) or for several intervals: n-1 launches, each advancing every chain of the batch by one step.
+  bool chains_done = false;
+  if (m == 1) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (cap != cudaStreamCaptureStatusActive) {
+      const int total = 2 * Hg * Wg;
+      int cgrid = (total + 255) / 256;
+      static int bps = blocks_per_sm(block_chain_coop_kernel<Nm>, 256);
+      const int capacity = sm_count() * bps;
+      if (cgrid > capacity) cgrid = capacity;
+      ChainGrids cgr;
+      for (int j = 0; j < n - 1; ++j) { cgr.left[j] = gl[j]; cgr.right[j] = gr[j]; }
+      const float* prev = keys[0];
+      const float* next = keys[1];
+      float* Lst = scratch;
+      float* Rst = scratch + (n - 1) * ls;
+      void* args[] = {(void*)&prev, (void*)&next, (void*)&cgr, (void*)&Lst, (void*)&Rst,
+                      (void*)&C, (void*)&H, (void*)&W, (void*)&Hg, (void*)&Wg, (void*)&n};
+      if (cudaLaunchCooperativeKernel((const void*)block_chain_coop_kernel<Nm>, dim3(cgrid), dim3(256), args, 0, st) ==
+          cudaSuccess) {
+        count_launch();
+        chains_done = true;
+      } else {
+        cudaGetLastError();   // cooperative launch unavailable: per-step launches below
       }
     }
   }
-  if (counts) return launch_temporal_counts(labels, n, HW, tc_prev, C, ignore_index, counts, st);
+  if (!chains_done) {
+    for (int i0 = 0; i0 < m; i0 += CHAIN_MAX_IV) {
+      const int mb = (m - i0 < CHAIN_MAX_IV) ? m - i0 : CHAIN_MAX_IV;
+      for (int j = 1; j <= n - 1; ++j) {
+        ChainStepBatch b;
+        for (int i = 0; i < mb; ++i) {
+          float* Lst = scratch + (i0 + i) * per_iv;
+          float* Rst = Lst + (n - 1) * ls;
+          b.src[2 * i] = (j == 1) ? keys[i0 + i] : Lst + (j - 2) * ls;
+          b.src[2 * i + 1] = (j == 1) ? keys[i0 + i + 1] : Rst + (j - 2) * ls;
+          b.grid[2 * i] = gl[(i0 + i) * (n - 1) + j - 1];
+          b.grid[2 * i + 1] = gr[(i0 + i) * (n - 1) + j - 1];
+          b.dst[2 * i] = Lst + (j - 1) * ls;
+          b.dst[2 * i + 1] = Rst + (j - 1) * ls;
+        }
+        const int Hin = (j == 1) ? H : Hg, Win = (j == 1) ? W : Wg;
+        dim3 cgrid((Wg + 31) / 32, (Hg + 7) / 8, 2 * mb), cblock(32, 8);
+        // plain launches on purpose: with programmatic stream serialization the early-launched CTAs of the later steps
+        // and of the frame kernel sit on the SMs the running step needs (r01: 97 vs 63 us per 1080p interval)
+        block_chain_step_kernel<Nm><<<cgrid, cblock, 0, st>>>(b, C, Hin, Win, Hg, Wg);
+        if (int e = check_launch("fuvs_block_interval(chain)")) return e;
+      }
+    }
+  }
+  // ---- frames of every interval
+  for (int i = 0; i < m; ++i) {
+    float* Lst = scratch + i * per_iv;
+    float* Rst = Lst + (n - 1) * ls;
+    uint8_t* lab = want_labels ? labels[i] : nullptr;
+    const uint8_t* tp = (i == 0) ? tc_prev : (want_labels ? labels[i - 1] + (n - 1) * HW : nullptr);
+    bool counts_done = false;
+    if (int e = block_frames(keys[i], Lst, Rst, C, H, W, Hg, Wg, n, lab, want_logits ? logits[i] : nullptr, tp, counts,
+                             ignore_index, st, &counts_done))
+      return e;
+    if (counts && !counts_done) {
+      if (int e = launch_temporal_counts(lab, n, HW, tp, C, ignore_index, counts, st)) return e;
+    }
+  }
   return FUVS_OK;
+}
+
+}  // namespace fuvs
+
+extern "C" int fuvs_block_interval_ptrs(const float* prev, const float* next, const float* const* grids_left,
+                                        const float* const* grids_right, int C, int H, int W, int Hg, int Wg, int n,
+                                        float* scratch, uint8_t* labels, float* logits, const uint8_t* tc_prev,
+                                        long long* counts, int ignore_index, fuvs_stream_t stream) {
+  const float* keys[2] = {prev, next};
+  uint8_t* labs[1] = {labels};
+  float* logs[1] = {logits};
+  if (n > 1 && !next) return fuvs::set_error(FUVS_EINVAL, "block: next key frame is NULL but n=%d", n);
+  return fuvs::block_clip_impl(1, keys, grids_left, grids_right, C, H, W, Hg, Wg, n, scratch, labs, logs, tc_prev, counts,
+                               ignore_index, static_cast<cudaStream_t>(stream), "block");
+}
+
+extern "C" int fuvs_block_interval(const float* prev, const float* next, const float* grids_left,
+                                   const float* grids_right, int C, int H, int W, int Hg, int Wg, int n,
+                                   float* scratch, uint8_t* labels, float* logits, const uint8_t* tc_prev,
+                                   long long* counts, int ignore_index, fuvs_stream_t stream) {
+  const float* gl[FUVS_MAX_FRAMES];
+  const float* gr[FUVS_MAX_FRAMES];
+  if (n > FUVS_MAX_FRAMES) return fuvs::set_error(FUVS_EINVAL, "block: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!grids_left || !grids_right)) return fuvs::set_error(FUVS_EINVAL, "block: grids are NULL but n=%d", n);
+  const long long g = static_cast<long long>(Hg) * Wg * 2;
+  for (int j = 0; j < n - 1; ++j) {
+    gl[j] = grids_left + j * g;
+    gr[j] = grids_right + j * g;
+  }
+  return fuvs_block_interval_ptrs(prev, next, gl, gr, C, H, W, Hg, Wg, n, scratch, labels, logits, tc_prev, counts,
+                                  ignore_index, stream);
+}
+
+extern "C" int fuvs_block_clip(int m, const float* const* keys, const float* const* grids_left,
+                               const float* const* grids_right, int C, int H, int W, int Hg, int Wg, int n,
+                               float* scratch, uint8_t* const* labels, float* const* logits, const uint8_t* tc_prev,
+                               long long* counts, int ignore_index, fuvs_stream_t stream) {
+  return fuvs::block_clip_impl(m, keys, grids_left, grids_right, C, H, W, Hg, Wg, n, scratch, labels, logits, tc_prev,
+                               counts, ignore_index, static_cast<cudaStream_t>(stream), "block_clip");
 }

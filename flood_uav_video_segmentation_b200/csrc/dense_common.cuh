@@ -19,6 +19,9 @@ struct DenseStep {
   float* logitA; float* logitB;
   // frame 0 on step 1
   const float* key0; uint8_t* label0; float* logit0;
+  // 1: the chain states of this interval (dst*, point*, and src* unless key0 is set) are stored "4+1" — channels 0-3
+  // interleaved per pixel ([H][W][4]) followed by the plane of channel 4 (C = 5, strip kernel only, dense_strip.cu)
+  int il;
 };
 
 // dense_tma.cu: returns FUVS_OK if it ran the step, 1 if the shape is not eligible (caller uses the direct kernel),
@@ -27,5 +30,8 @@ int launch_dense_step_tma(const DenseStep& a, int C, int H, int W, cudaStream_t 
 
 // dense_strip.cu (column-strip sliding window, all channels resident in shared memory): same return convention.
 int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_t st);
+// true if every step of the interval can run on the strip kernel with 4+1 chain states (decided once per interval)
+bool dense_strip_il_ok(int C, int H, int W, int n, const float* prev, const float* next, const float* gridsL,
+                       const float* gridsR, const float* scratch);
 
 }  // namespace fuvs

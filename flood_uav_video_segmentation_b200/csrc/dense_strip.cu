@@ -29,6 +29,12 @@
 //              pipe per block instead of the four dependent ones ptxas produced when it sank loads under the store
 //              predicates), then the FMA chains, blends and stores.  Full-size shapes (W % 128 == 0, H % 8 == 0)
 //              compile without per-pixel validity predicates.
+//   layout   : (r02) C = 5, odd n: the chain states in the scratch (never seen by the caller) are stored "4+1":
+//              channels 0-3 interleaved per pixel ([H][W][4]) followed by channel 4 as a plane.  A tap is then one
+//              128-bit + one 32-bit shared-memory load instead of five 32-bit ones (16 instead of 40 loads per block
+//              and thread, ~13 % fewer shared-memory cycles with per-pixel random flow: tools/probes/lds_gather_probe.cu),
+//              a state write one 128-bit + one 32-bit store, the pointwise operand likewise.  Step 1 reads the caller's
+//              planar key frames and writes 4+1; measured 239 -> 22x us per interval.
 //   taps     : a warp whose taps leave the window (large motion) gathers its pixels of that block from global memory
 //              instead, so any flow field stays correct.
 //   counts   : stay in fuvs_temporal_counts (metric.cu).
@@ -73,8 +79,8 @@ struct StripGeom {
   int wstart;                                // extra cost of the first block of a strip, in eighths of a block
 };
 struct StripMaps {
-  CUtensorMap srcL, srcR;                    // [C][H][W] fp32, box BOXW x RB x 1
-};
+  CUtensorMap srcL, srcR;                    // planar [C][H][W] fp32, box BOXW x RB x 1 (4+1 sources: the plane of channel 4;
+};                                           // their interleaved part comes in row-wise bulk copies, see issue())
 
 template <int... I, class F>
 __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F&& f) {
@@ -92,6 +98,12 @@ __device__ __forceinline__ float lds_imm(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
   return v;
 }
+template <int OFF>
+__device__ __forceinline__ float4 lds4_imm(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+  return v;
+}
 __device__ __forceinline__ float lds_rt(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -106,9 +118,14 @@ __device__ __forceinline__ unsigned atom_add_relaxed(uint32_t addr, unsigned v) 
   return old;
 }
 
+// Element (channel c, pixel off) of a state: planar [C][HW], or 4+1 (channels 0-3 interleaved, channel 4 a plane).
+__device__ __forceinline__ long long state_index(bool il, int c, long long off, long long HW) {
+  return il ? (c < 4 ? off * 4 + c : 4 * HW + off) : c * HW + off;
+}
+
 // Rare path: the warp computes its pixels of this block straight from global memory (same math as warp.cu).
 __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap, bool side, bool emit, bool key0, int C,
-                                               int H, int W, int x, int ytop, unsigned valid) {
+                                               int H, int W, int x, int ytop, unsigned valid, bool il, bool il_src) {
   const DenseStep& A = *Ap;
   const long long HW = static_cast<long long>(H) * W;
   const float* grid = side ? A.gridR : A.gridL;
@@ -128,10 +145,14 @@ __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap,
     am0.init(-INFINITY);
     for (int c = 0; c < C; ++c) {
       const long long o = c * HW + pix;
-      const float acc = gs_fetch<Nm>(src + c * HW, t, W);
-      if (dst) dst[o] = acc;
+      const long long n0 = t.off00, n1 = n0 + t.dx, s0 = n0 + static_cast<long long>(t.dy) * W, s1 = s0 + t.dx;
+      float acc = tap_acc<Nm>(0.f, __ldg(src + state_index(il_src, c, n0, HW)), t.nw);
+      if (t.dx) acc = tap_acc<Nm>(acc, __ldg(src + state_index(il_src, c, n1, HW)), t.ne);
+      if (t.dy) acc = tap_acc<Nm>(acc, __ldg(src + state_index(il_src, c, s0, HW)), t.sw);
+      if (t.dx & t.dy) acc = tap_acc<Nm>(acc, __ldg(src + state_index(il_src, c, s1, HW)), t.se);
+      if (dst) dst[state_index(il, c, pix, HW)] = acc;
       if (emit) {
-        const float other = __ldg(point + o);
+        const float other = __ldg(point + state_index(il, c, pix, HW));
         const float v = blend2(w_this, acc, w_point, other);
         am.push(v, c);
         if (logit_out) __stcs(logit_out + o, v);
@@ -152,11 +173,14 @@ __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap,
 //   WDST   : the step writes its states (every step but the last)
 //   FULLV  : W % 128 == 0 and H % 8 == 0: every pixel of every block exists
 //   NSC    : ring slots when known at compile time (0: G.nslot)
-template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV>
+//   IL     : C = 5 only: the states of this interval (dst, pointwise operand, and the source unless KEY0) are 4+1
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
                    StripGeom G) {
   static_assert(!(EMIT && KEY0), "frame 0 and a completed frame never share a step here (the host routes n<=2 elsewhere)");
+  static_assert(!IL || CT == 5, "the 4+1 state layout exists for C = 5");
+  constexpr bool SIL = IL && !KEY0;              // the source window is 4+1: [ring row][x][4] then the plane of channel 4
   constexpr int CR = CT > 0 ? CT : 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : Crt;
@@ -249,11 +273,25 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
       if (ytop + RB <= 0 || ytop >= H) {
         mbar_arrive(bar);                    // slot entirely outside the image: never read (border clipping)
       } else {
-        mbar_expect_tx(bar, slot_bytes);
-        const uint32_t dst = ring0 + static_cast<uint32_t>(b * PLANE) * 4u;
         const int bx = box_x(strip);
-        for (int c = 0; c < C; ++c)
-          load_3d(dst + static_cast<uint32_t>(c * chan_floats) * 4u, side ? &M.srcR : &M.srcL, bx, ytop, c, bar);
+        if (SIL) {
+          // channels 0-3: one window row is 192 x 16 contiguous bytes of the [H][W][4] part -> one bulk copy per row
+          // that exists (a tensor box with a 16-byte inner extent would be split into 16-byte requests); channel 4:
+          // one box of its plane (rows outside the image are zero-filled and count as transferred)
+          const int r0 = max(0, -ytop), r1 = min(RB, H - ytop);
+          const uint32_t rowb = static_cast<uint32_t>(min(BOXW, W - bx)) * 16u;
+          mbar_expect_tx(bar, static_cast<uint32_t>(r1 - r0) * rowb + PLANE * 4u);
+          const float* q = side ? A.srcR : A.srcL;
+          for (int r = r0; r < r1; ++r)
+            load_bulk(ring0 + static_cast<uint32_t>(b * PLANE + r * BOXW) * 16u,
+                      q + (static_cast<long long>(ytop + r) * W + bx) * 4, rowb, bar);
+          load_3d(ring0 + static_cast<uint32_t>(4 * chan_floats + b * PLANE) * 4u, side ? &M.srcR : &M.srcL, bx, ytop, 0, bar);
+        } else {
+          mbar_expect_tx(bar, slot_bytes);
+          const uint32_t dst = ring0 + static_cast<uint32_t>(b * PLANE) * 4u;
+          for (int c = 0; c < C; ++c)
+            load_3d(dst + static_cast<uint32_t>(c * chan_floats) * 4u, side ? &M.srcR : &M.srcL, bx, ytop, c, bar);
+        }
       }
       return true;
     });
@@ -307,8 +345,14 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
       for (int r = 0; r < PX; ++r) {
         const int y = yb + ty + r * TROWS;
         const bool live = on && vx && (FULLV || y < H);
+        if constexpr (IL) {
+          const float4 q = live ? __ldg(reinterpret_cast<const float4*>(point) + (y * W + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dsto[r][0] = q.x; dsto[r][1] = q.y; dsto[r][2] = q.z; dsto[r][3] = q.w;
+          dsto[r][CR - 1] = live ? __ldg(point + (4 * HWi + y * W + x)) : 0.f;
+        } else {
 #pragma unroll
-        for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldg(point + (c * HWi + y * W + x)) : 0.f;
+          for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldg(point + (c * HWi + y * W + x)) : 0.f;
+        }
       }
     };
     // two alternating register sets: block jj uses set jj & 1.  Flow vectors of block jj+2 are loaded into the set of
@@ -367,11 +411,12 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
           if (live[r] && !in_box) outside = true;
           unsigned rr = d + static_cast<unsigned>(rb0);
           rr = min(rr, rr - static_cast<unsigned>(NSR));            // wrap: rr - NSR is huge when rr < NSR
-          const uint32_t a = ring0 + (rr * BOXW + lx) * 4u;
-          aN[r] = in_box ? a : ring0;
-          aS[r] = in_box ? ((rr == static_cast<unsigned>(NSR - 1)) ? a - static_cast<uint32_t>((NSR - 1) * BOXW) * 4u
-                                                                    : a + BOXW * 4u)
-                         : ring0;
+          // ring element (row, column) of the north-west tap and of the one below it; byte addresses are formed at
+          // the loads (x4 planar, x16 and x4 for the two parts of a 4+1 window)
+          const unsigned e = rr * BOXW + lx;
+          aN[r] = in_box ? e : 0u;
+          aS[r] = in_box ? ((rr == static_cast<unsigned>(NSR - 1)) ? e - static_cast<unsigned>((NSR - 1) * BOXW) : e + BOXW)
+                         : 0u;
         }
         // ---- this set's flow vectors are consumed: refill it for block jj + 2 (nothing here depends on the ring)
         load_grid(y0 + 2 * RB, jj + 2 < nb, g);
@@ -397,7 +442,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
           unsigned valid = 0u;
 #pragma unroll
           for (int r = 0; r < PX; ++r) valid |= (live[r] ? 1u : 0u) << r;
-          block_from_global(&A, side, EMIT, do_key0, C, H, W, x, y0 + ty, valid);
+          block_from_global(&A, side, EMIT, do_key0, C, H, W, x, y0 + ty, valid, IL, SIL);
         } else {
           const bool w_dst = WDST && dst != nullptr;
           const bool w_lp = EMIT && logit_out != nullptr;
@@ -420,16 +465,34 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
             // ---- one burst: every tap of both pixels (4 CT loads each), then the key-frame values
             float v[PX][CT][4];
             float vk[PX][CT];
-            static_for<PX>([&](auto r_) {
-              constexpr int r = decltype(r_)::value;
-              static_for<CT>([&](auto c_) {
-                constexpr int c = decltype(c_)::value;
-                v[r][c][0] = lds_imm<c * CHB>(aN[r]);
-                v[r][c][1] = lds_imm<c * CHB + 4>(aN[r]);
-                v[r][c][2] = lds_imm<c * CHB>(aS[r]);
-                v[r][c][3] = lds_imm<c * CHB + 4>(aS[r]);
+            if constexpr (SIL) {
+              static_for<PX>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const uint32_t qn = ring0 + aN[r] * 16u, qs = ring0 + aS[r] * 16u;
+                const uint32_t pn = ring0 + 4u * CHB + aN[r] * 4u, ps = ring0 + 4u * CHB + aS[r] * 4u;
+                const float4 t0 = lds4_imm<0>(qn), t1 = lds4_imm<16>(qn), t2 = lds4_imm<0>(qs), t3 = lds4_imm<16>(qs);
+                v[r][0][0] = t0.x; v[r][1][0] = t0.y; v[r][2][0] = t0.z; v[r][3][0] = t0.w;
+                v[r][0][1] = t1.x; v[r][1][1] = t1.y; v[r][2][1] = t1.z; v[r][3][1] = t1.w;
+                v[r][0][2] = t2.x; v[r][1][2] = t2.y; v[r][2][2] = t2.z; v[r][3][2] = t2.w;
+                v[r][0][3] = t3.x; v[r][1][3] = t3.y; v[r][2][3] = t3.z; v[r][3][3] = t3.w;
+                v[r][4][0] = lds_imm<0>(pn);
+                v[r][4][1] = lds_imm<4>(pn);
+                v[r][4][2] = lds_imm<0>(ps);
+                v[r][4][3] = lds_imm<4>(ps);
               });
-            });
+            } else {
+              static_for<PX>([&](auto r_) {
+                constexpr int r = decltype(r_)::value;
+                const uint32_t an = ring0 + aN[r] * 4u, as = ring0 + aS[r] * 4u;
+                static_for<CT>([&](auto c_) {
+                  constexpr int c = decltype(c_)::value;
+                  v[r][c][0] = lds_imm<c * CHB>(an);
+                  v[r][c][1] = lds_imm<c * CHB + 4>(an);
+                  v[r][c][2] = lds_imm<c * CHB>(as);
+                  v[r][c][3] = lds_imm<c * CHB + 4>(as);
+                });
+              });
+            }
             if (KEY0 && do_key0) {
               static_for<PX>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
@@ -443,6 +506,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 #pragma unroll
             for (int r = 0; r < PX; ++r) {
               const bool dxy = pdx[r] && pdy[r];
+              float accs[CT];
 #pragma unroll
               for (int c = 0; c < CT; ++c) {
                 const int gi = c * HWi + pix0 + r * rstride;
@@ -450,7 +514,8 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
                 if (pdx[r]) acc = tap_acc<Nm>(acc, v[r][c][1], wne[r]);
                 if (pdy[r]) acc = tap_acc<Nm>(acc, v[r][c][2], wsw[r]);
                 if (dxy) acc = tap_acc<Nm>(acc, v[r][c][3], wse[r]);
-                if (w_dst && live[r]) dst[gi] = acc;
+                accs[c] = acc;
+                if (!IL && w_dst && live[r]) dst[gi] = acc;
                 if (EMIT) {
                   // fl(fl(w_this*acc) + fl(w_point*o)): IEEE addition is commutative, so one operand order serves both
                   // sides (the reference adds the forward term first on both) and the code is not duplicated per side
@@ -463,6 +528,13 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
                   if (w_l0 && live[r]) __stcs(A.logit0 + gi, vk[r][c]);
                 }
               }
+              if constexpr (IL) {
+                if (w_dst && live[r]) {
+                  const int pix = pix0 + r * rstride;
+                  reinterpret_cast<float4*>(dst)[pix] = make_float4(accs[0], accs[1], accs[2], accs[3]);
+                  dst[4 * HWi + pix] = accs[CT - 1];
+                }
+              }
             }
           } else {
             const uint32_t chb = static_cast<uint32_t>(chan_floats) * 4u;
@@ -471,8 +543,9 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
               const bool dxy = pdx[r] && pdy[r];
               for (int c = 0; c < C; ++c) {
                 const uint32_t co = static_cast<uint32_t>(c) * chb;
-                const float v00 = lds_rt(aN[r] + co), v01 = lds_rt(aN[r] + co + 4u);
-                const float v10 = lds_rt(aS[r] + co), v11 = lds_rt(aS[r] + co + 4u);
+                const uint32_t an = ring0 + aN[r] * 4u + co, as = ring0 + aS[r] * 4u + co;
+                const float v00 = lds_rt(an), v01 = lds_rt(an + 4u);
+                const float v10 = lds_rt(as), v11 = lds_rt(as + 4u);
                 const int gi = c * HWi + pix0 + r * rstride;
                 float acc = tap_acc<Nm>(0.f, v00, wnw[r]);
                 if (pdx[r]) acc = tap_acc<Nm>(acc, v01, wne[r]);
@@ -523,12 +596,12 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
   refill_if_last();                                // nothing left to load for this CTA: issue() ignores indices past the end
 }
 
-template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV>
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
 int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   static SmemOptIn optin;
-  auto kern = dense_strip_kernel<CT, NSC, EMIT, KEY0, WDST, FULLV>;
+  auto kern = dense_strip_kernel<CT, NSC, EMIT, KEY0, WDST, FULLV, IL>;
   const size_t smem = static_cast<size_t>(nslot) * C * PLANE * 4 + 256;
-  if (!optin.ensure(kern, SMEM_LIMIT)) return 1;
+  if (!optin.ensure(kern, SMEM_LIMIT)) return set_error(FUVS_ECUDA, "fuvs_dense_interval(strip step): shared-memory opt-in failed");
   StripGeom g;
   g.nsx = (W + TW - 1) / TW;
   g.nby = (H + RB - 1) / RB;
@@ -556,42 +629,70 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   return FUVS_OK;
 }
 
-template <int CT, int NSC, bool FULLV>
+template <int CT, int NSC, bool FULLV, bool IL>
 int launch_ct(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   const bool wdst = a.dstL != nullptr;
   if (a.emitA) {
-    return wdst ? launch_variant<CT, NSC, true, false, true, FULLV>(maps, a, C, H, W, nslot, st)
-                : launch_variant<CT, NSC, true, false, false, FULLV>(maps, a, C, H, W, nslot, st);
+    return wdst ? launch_variant<CT, NSC, true, false, true, FULLV, IL>(maps, a, C, H, W, nslot, st)
+                : launch_variant<CT, NSC, true, false, false, FULLV, IL>(maps, a, C, H, W, nslot, st);
   }
-  if (a.key0) return launch_variant<CT, NSC, false, true, true, FULLV>(maps, a, C, H, W, nslot, st);
-  return launch_variant<CT, NSC, false, false, true, FULLV>(maps, a, C, H, W, nslot, st);
+  if (a.key0) return launch_variant<CT, NSC, false, true, true, FULLV, IL>(maps, a, C, H, W, nslot, st);
+  return launch_variant<CT, NSC, false, false, true, FULLV, IL>(maps, a, C, H, W, nslot, st);
 }
 
 template <bool FULLV>
 int launch_full(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   switch (C) {
-    case 2: return launch_ct<2, NSLOT_C2, FULLV>(maps, a, C, H, W, nslot, st);
-    case 5: return launch_ct<5, NSLOT_C5, FULLV>(maps, a, C, H, W, nslot, st);
-    default: return launch_ct<0, 0, FULLV>(maps, a, C, H, W, nslot, st);
+    case 2: return launch_ct<2, NSLOT_C2, FULLV, false>(maps, a, C, H, W, nslot, st);
+    case 5:
+      return a.il ? launch_ct<5, NSLOT_C5, FULLV, true>(maps, a, C, H, W, nslot, st)
+                  : launch_ct<5, NSLOT_C5, FULLV, false>(maps, a, C, H, W, nslot, st);
+    default: return launch_ct<0, 0, FULLV, false>(maps, a, C, H, W, nslot, st);
   }
+}
+
+bool shape_ok(int C, int H, int W) {
+  return (W & 3) == 0 && W >= 4 && H < 32768 && W < 32768 && C <= 16 && static_cast<long long>(C) * H * W < (1ll << 31) &&
+         nslot_for(C) >= WIN + 1;
 }
 
 }  // namespace
 
-// Returns FUVS_OK if it ran the step, 1 if the shape is not eligible (the caller falls back), negative on error.
+// Can every step of an n-frame interval run on the strip kernel with the chain states stored 4+1 (see `layout` above)?
+// The caller (fuvs_dense_interval) decides once per interval: a state written 4+1 must be read 4+1.
+bool dense_strip_il_ok(int C, int H, int W, int n, const float* prev, const float* next, const float* gridsL,
+                       const float* gridsR, const float* scratch) {
+  return C == 5 && n >= 3 && (n & 1) == 1 && shape_ok(C, H, W) && aligned16(prev) && aligned16(next) &&
+         aligned16(scratch) && aligned8(gridsL) && aligned8(gridsR) && get_encode() != nullptr;
+}
+
+// Returns FUVS_OK if it ran the step, 1 if the shape is not eligible (the caller falls back; never for a.il steps, whose
+// eligibility dense_strip_il_ok has established), negative on error.
 int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_t st) {
-  if ((W & 3) != 0 || W < 4 || !aligned16(a.srcL) || !aligned16(a.srcR) || H >= 32768 || W >= 32768) return 1;
-  if ((a.emitA && !a.pointR) || (a.emitB && !a.pointL) || (a.emitA != a.emitB)) return 1;
-  if (a.key0 && (a.key0 != a.srcL || a.emitA)) return 1;
-  if ((a.dstL != nullptr) != (a.dstR != nullptr)) return 1;
-  if (!a.emitA && !a.dstL) return 1;             // a step that neither writes states nor emits frames does not exist
-  if (!aligned8(a.gridL) || !aligned8(a.gridR)) return 1;
-  if (C > 16 || static_cast<long long>(C) * H * W >= (1ll << 31)) return 1;
+  // not eligible: the caller falls back to another kernel, which is not possible for a step whose states are 4+1
+  auto ineligible = [&]() {
+    return a.il ? set_error(FUVS_EINVAL, "fuvs_dense_interval: a 4+1 step is not eligible for the strip kernel") : 1;
+  };
+  if (!shape_ok(C, H, W) || !aligned16(a.srcL) || !aligned16(a.srcR)) return ineligible();
+  if ((a.emitA && !a.pointR) || (a.emitB && !a.pointL) || (a.emitA != a.emitB)) return ineligible();
+  if (a.key0 && (a.key0 != a.srcL || a.emitA)) return ineligible();
+  if ((a.dstL != nullptr) != (a.dstR != nullptr)) return ineligible();
+  if (!a.emitA && !a.dstL) return ineligible();           // a step that neither writes states nor emits frames does not exist
+  if (!aligned8(a.gridL) || !aligned8(a.gridR)) return ineligible();
+  if (a.il && C != 5) return ineligible();
   const int nslot = nslot_for(C);
-  if (nslot < WIN + 1) return 1;                 // the window of all channels does not fit: per-plane kernel
   StripMaps maps;
-  if (!make_map_chw(&maps.srcL, a.srcL, C, H, W, BOXW, RB, 1) || !make_map_chw(&maps.srcR, a.srcR, C, H, W, BOXW, RB, 1))
-    return 1;
+  const bool sil = a.il && !a.key0;
+  const long long HW = static_cast<long long>(H) * W;
+  if (sil) {
+    // 4+1 source: channels 0-3 interleaved, channel 4 a plane behind them
+    if (!make_map_chw(&maps.srcL, a.srcL + 4 * HW, 1, H, W, BOXW, RB, 1) ||
+        !make_map_chw(&maps.srcR, a.srcR + 4 * HW, 1, H, W, BOXW, RB, 1))
+      return ineligible();
+  } else {
+    if (!make_map_chw(&maps.srcL, a.srcL, C, H, W, BOXW, RB, 1) || !make_map_chw(&maps.srcR, a.srcR, C, H, W, BOXW, RB, 1))
+      return ineligible();
+  }
   if ((W % TW) == 0 && (H % RB) == 0) return launch_full<true>(maps, a, C, H, W, nslot, st);
   return launch_full<false>(maps, a, C, H, W, nslot, st);
 }

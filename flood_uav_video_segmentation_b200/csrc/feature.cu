@@ -162,6 +162,22 @@ extern "C" long long fuvs_feature_scratch_floats(int C, int Hg, int Wg, int Hd, 
 extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, const float* grids_left,
                                      const float* grids_right, const float* default_grid, int Hd, int Wd, int C, int fh,
                                      int fw, int Hg, int Wg, int n, float* scratch, float* out, fuvs_stream_t stream) {
+  const float* gl[FUVS_MAX_FRAMES];
+  const float* gr[FUVS_MAX_FRAMES];
+  if (n > FUVS_MAX_FRAMES) return fuvs::set_error(FUVS_EINVAL, "feature_interval: n=%d exceeds %d frames", n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!grids_left || !grids_right)) return fuvs::set_error(FUVS_EINVAL, "feature_interval: grids missing but n=%d", n);
+  const long long g = static_cast<long long>(Hg) * Wg * 2;
+  for (int j = 0; j < n - 1; ++j) {
+    gl[j] = grids_left + j * g;
+    gr[j] = grids_right + j * g;
+  }
+  return fuvs_feature_interval_ptrs(f_prev, f_next, gl, gr, default_grid, Hd, Wd, C, fh, fw, Hg, Wg, n, scratch, out, stream);
+}
+
+extern "C" int fuvs_feature_interval_ptrs(const float* f_prev, const float* f_next, const float* const* grids_left,
+                                          const float* const* grids_right, const float* default_grid, int Hd, int Wd,
+                                          int C, int fh, int fw, int Hg, int Wg, int n, float* scratch, float* out,
+                                          fuvs_stream_t stream) {
   using namespace fuvs;
   if (int e = device_ok()) return e;
   if (!f_prev || !out || C < 1 || fh < 1 || fw < 1 || n < 1)
@@ -174,8 +190,12 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
   const long long plane = static_cast<long long>(fh) * fw;
   if (plane >= (1ll << 31) || static_cast<long long>(C) * Hg * Wg >= (1ll << 31))
     return set_error(FUVS_EINVAL, "feature_interval: problem exceeds 32-bit indexing");
-  if ((n > 1 && (!aligned8(grids_left) || !aligned8(grids_right))) || (default_grid && !aligned8(default_grid)))
-    return set_error(FUVS_EALIGN, "feature_interval: grids must be 8-byte aligned");
+  for (int j = 0; n > 1 && j < n - 1; ++j) {
+    if (!grids_left[j] || !grids_right[j]) return set_error(FUVS_EINVAL, "feature_interval: grid %d is NULL", j);
+    if (!aligned8(grids_left[j]) || !aligned8(grids_right[j]))
+      return set_error(FUVS_EALIGN, "feature_interval: grids must be 8-byte aligned");
+  }
+  if (default_grid && !aligned8(default_grid)) return set_error(FUVS_EALIGN, "feature_interval: grids must be 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long S = static_cast<long long>(C) * plane;
   const long long ls = static_cast<long long>(C) * Hg * Wg;
@@ -189,9 +209,8 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
       const float* sL = (j == 1) ? f_prev : Lst + (j - 2) * ls;
       const float* sR = (j == 1) ? f_next : Rst + (j - 2) * ls;
       const int Hin = (j == 1) ? fh : Hg, Win = (j == 1) ? fw : Wg;
-      if (int e = launch_warp_step_nm(sL, grids_left + static_cast<long long>(j - 1) * Hg * Wg * 2, Lst + (j - 1) * ls, sR,
-                                      grids_right + static_cast<long long>(j - 1) * Hg * Wg * 2, Rst + (j - 1) * ls, C, Hin,
-                                      Win, Hg, Wg, 0, st))
+      if (int e = launch_warp_step_nm(sL, grids_left[j - 1], Lst + (j - 1) * ls, sR, grids_right[j - 1], Rst + (j - 1) * ls,
+                                      C, Hin, Win, Hg, Wg, 0, st))
         return e;
     }
     BlendWeights w;
@@ -208,13 +227,12 @@ extern "C" int fuvs_feature_interval(const float* f_prev, const float* f_next, c
       const float sw = fw > 1 ? static_cast<float>(Wg - 1) / (fw - 1) : 0.f;
       const bool vec4 = (fw % 4 == 0) && aligned16(out);
       // staged kernel: bands of source rows sized for four CTAs per SM (2 states x (rows + 1) x fw floats <= 48 KB)
-      static const bool staged = []() { const char* e = getenv("FUVS_FEATURE_STAGED"); return !(e && e[0] == '0'); }();
       int band_rows = static_cast<int>((46 * 1024) / (8ll * fw)) - 1;          // 2 KB of the 48 KB for the row table
       if (band_rows > Hg) band_rows = Hg;
       long long nb = band_rows >= 1 ? (Hg + band_rows - 1) / band_rows : 0;
       if (nb > 0) band_rows = static_cast<int>((Hg + nb - 1) / nb);            // equal bands
       const long long ctas = nb * C * (n - 1);
-      if (staged && vec4 && band_rows >= 1 && ctas <= 0x7fffffffll && fh > 1 && fw > 1) {
+      if (vec4 && band_rows >= 1 && ctas <= 0x7fffffffll && fh > 1 && fw > 1) {
         // + the row table: a band of band_rows source rows covers at most band_rows (fh-1)/(Hg-1) + 2 output rows
         const long long mo = (fh > 1 && Hg > 1) ? (static_cast<long long>(band_rows) * (fh - 1) + Hg - 2) / (Hg - 1) + 2 : fh;
         const size_t smem = static_cast<size_t>(2) * (band_rows + 1) * fw * sizeof(float) + static_cast<size_t>(mo < fh ? mo : fh) * 16;

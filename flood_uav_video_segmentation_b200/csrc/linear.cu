@@ -521,12 +521,6 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
   if (COUNTS) cnt.finish(sh, counts, CT);
 }
 
-// FUVS_LINEAR_NQ = 1 | 4 slice pipelines per CTA, FUVS_LINEAR_PDL = 0 | 1 (A/B switches; defaults from measurements)
-static int linear_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
-}
-
 template <int CT, bool COUNTS, bool LOGITS, int NQ, int NP>
 static int launch_bulk_nq(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                           const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
@@ -535,7 +529,7 @@ static int launch_bulk_nq(const float* prev, const float* next, long long HW, in
   auto kern = linear_blend_argmax_bulk_kernel<CT, COUNTS, LOGITS, NQ, NP>;
   static SmemOptIn optin;
   if (!optin.ensure(kern, static_cast<int>(smem))) return 1;   // caller uses the register-load kernel
-  static const int pdl = linear_env("FUVS_LINEAR_PDL", 1);
+  constexpr int pdl = 1;                       // programmatic dependent launch (r01: 23.5 -> 22.5 us per interval)
   const long long ntiles = (HW + BULK_TILE - 1) / BULK_TILE;
   const long long cap = sm_count();
   const int grid = static_cast<int>(ntiles < cap ? ntiles : cap);
@@ -549,21 +543,19 @@ static int launch_bulk_nq(const float* prev, const float* next, long long HW, in
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, prev, next, HW, n, labels, logits, tc_prev, reinterpret_cast<unsigned long long*>(counts),
-                     ignore_index, w, 1.0f, pdl);
-  return check_launch("fuvs_linear_blend_argmax(bulk)");
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prev, next, HW, n, labels, logits, tc_prev,
+                                           reinterpret_cast<unsigned long long*>(counts), ignore_index, w, 1.0f, pdl);
+  if (e != cudaSuccess) return set_error(FUVS_ECUDA, "fuvs_linear_blend_argmax(bulk): %s", cudaGetErrorString(e));
+  count_launch();
+  return FUVS_OK;
 }
 
 template <int CT, bool COUNTS, bool LOGITS>
 static int launch_bulk(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                        const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                        cudaStream_t st) {
-  static const int nq = linear_env("FUVS_LINEAR_NQ", 1);
-  static const int px = linear_env("FUVS_LINEAR_BULK_PX", 4);       // 4 pixels x 512 threads | 2 pixels x 1024 threads
-  if (nq == 4) return launch_bulk_nq<CT, COUNTS, LOGITS, 4, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-  if (px == 2) return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 1>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-  if (px == 8 && HW % 8 == 0 && aligned8(labels) && aligned8(tc_prev) && (!logits || aligned16(logits)))
-    return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 4>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+  // one pipeline per CTA, 4 pixels x 512 threads: the optimum of the r01 sweep (2 px x 1024 threads 25.9 us, 8 px x 256
+  // threads 21.7 us, four 512-pixel slice pipelines 24.0 us, against 20.8 us)
   return launch_bulk_nq<CT, COUNTS, LOGITS, 1, 2>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
 }
 
@@ -777,19 +769,12 @@ static int launch_v4(const float* prev, const float* next, long long HW, int n, 
   return check_launch("fuvs_linear_blend_argmax");
 }
 
-// FUVS_LINEAR_PX = 2 | 4 pixels per thread (A/B switch; default chosen from measurements on the B200)
-static int linear_px() {
-  static const int v = []() { const char* e = getenv("FUVS_LINEAR_PX"); return (e && e[0] == '4') ? 4 : (e && e[0] == '2') ? 2 : 0; }();
-  return v;
-}
-
 template <int CT, int VEC>
 static int launch_fixed(const float* prev, const float* next, long long HW, int n, uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts, int ignore_index, const BlendWeights& w,
                         cudaStream_t st) {
   if (VEC == 4 && (ignore_index < 0 || ignore_index >= CT)) {
-    static const bool want_bulk = []() { const char* e = getenv("FUVS_LINEAR_KERNEL"); return !(e && e[0] == 'r'); }();
-    if (want_bulk && CT <= 5 && HW >= 4 * BULK_TILE) {
+    if (CT <= 5 && HW >= 4 * BULK_TILE) {
       constexpr int CB = CT <= 5 ? CT : 2;
       int r;
       if (logits)
@@ -800,13 +785,9 @@ static int launch_fixed(const float* prev, const float* next, long long HW, int 
                    : launch_bulk<CB, false, false>(prev, next, HW, n, labels, nullptr, nullptr, nullptr, ignore_index, w, st);
       if (r <= 0) return r;
     }
-    const int px = linear_px() ? linear_px() : 4;
-    if (px == 4) {
-      if (counts) return launch_v4<CT, 2, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-      return launch_v4<CT, 2, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
-    }
-    if (counts) return launch_v4<CT, 1, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
-    return launch_v4<CT, 1, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
+    // small frames, C > 5, or no shared-memory opt-in: register-load kernel, 4 pixels per thread
+    if (counts) return launch_v4<CT, 2, true>(prev, next, HW, n, labels, logits, tc_prev, counts, ignore_index, w, st);
+    return launch_v4<CT, 2, false>(prev, next, HW, n, labels, logits, nullptr, nullptr, ignore_index, w, st);
   }
   const long long nvec = HW / VEC;
   const int threads = 256;

@@ -398,7 +398,7 @@ static int launch_confusion_v16(void* pred, const void* target, long long nunits
   constexpr bool IL = conf_interleaved<PT, TT>();
   const long long work_threads = IL ? nunits * 32 : nunits;
   // software pipelining only for byte labels: with int64 operands two groups in flight do not fit the registers
-  static const bool pipe = []() { const char* e = getenv("FUVS_CONF_PIPE"); return !(e && e[0] == '0'); }();
+  constexpr bool pipe = true;
 #define FUVS_CF16(KT_)                                                                                         \
   {                                                                                                            \
     bool launched = false;                                                                                     \

@@ -48,6 +48,12 @@ __device__ __forceinline__ void load_3d(uint32_t dst, const CUtensorMap* map, in
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
       : "memory");
 }
+// 1-D bulk copy (UBLKCP): `bytes` (multiple of 16) from 16-byte aligned global memory, completion on an mbarrier
+__device__ __forceinline__ void load_bulk(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"

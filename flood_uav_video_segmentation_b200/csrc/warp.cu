@@ -194,6 +194,22 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
                                    const float* grids_right, int C, int H, int W, int n, float* scratch,
                                    uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
                                    int ignore_index, fuvs_stream_t stream) {
+  const float* gl[FUVS_MAX_FRAMES];
+  const float* gr[FUVS_MAX_FRAMES];
+  if (n > FUVS_MAX_FRAMES) return fuvs::set_error(FUVS_EINVAL, "dense: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
+  if (n > 1 && (!grids_left || !grids_right)) return fuvs::set_error(FUVS_EINVAL, "dense: next/grids are NULL but n=%d", n);
+  const long long g = static_cast<long long>(H) * W * 2;
+  for (int j = 0; j < n - 1; ++j) {
+    gl[j] = grids_left + j * g;
+    gr[j] = grids_right + j * g;
+  }
+  return fuvs_dense_interval_ptrs(prev, next, gl, gr, C, H, W, n, scratch, labels, logits, tc_prev, counts, ignore_index, stream);
+}
+
+extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, const float* const* grids_left,
+                                        const float* const* grids_right, int C, int H, int W, int n, float* scratch,
+                                        uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
+                                        int ignore_index, fuvs_stream_t stream) {
   using namespace fuvs;
   if (int e = device_ok()) return e;
   if (!prev || C < 1 || H < 1 || W < 1 || n < 1) return set_error(FUVS_EINVAL, "dense: bad shape C=%d H=%d W=%d n=%d", C, H, W, n);
@@ -204,7 +220,10 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
   if (counts && !labels) return set_error(FUVS_EINVAL, "dense: counts need the label maps (labels is NULL)");
   const long long HW = static_cast<long long>(H) * W;
   if (HW >= (1ll << 31)) return set_error(FUVS_EINVAL, "dense: plane exceeds 2^31 elements");
-  if (n > 1 && (!aligned8(grids_left) || !aligned8(grids_right))) return set_error(FUVS_EALIGN, "dense: grids must be 8-byte aligned");
+  for (int j = 0; n > 1 && j < n - 1; ++j) {
+    if (!grids_left[j] || !grids_right[j]) return set_error(FUVS_EINVAL, "dense: grid %d is NULL", j);
+    if (!aligned8(grids_left[j]) || !aligned8(grids_right[j])) return set_error(FUVS_EALIGN, "dense: grids must be 8-byte aligned");
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long S = static_cast<long long>(C) * HW;
 
@@ -219,21 +238,20 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
   } else {
     BlendWeights w;
     make_blend_weights(n, &w);
-    // FUVS_DENSE_KERNEL selects the step kernel for A/B measurements: "strip" (default: sliding-window TMA kernel,
-    // dense_strip.cu), "plane" (per-plane TMA kernel, dense_tma.cu), "direct" (L1 gather, this file).  Shapes a
-    // kernel cannot take fall through to the next one.
-    static const int kernel_sel = []() {
-      const char* e = getenv("FUVS_DENSE_KERNEL");
-      return (e && e[0] == 'd') ? 2 : (e && e[0] == 'p') ? 1 : 0;
-    }();
+    // Step kernels, in order of preference: strip (sliding-window TMA kernel, dense_strip.cu), plane (per-plane TMA
+    // kernel, dense_tma.cu: C > 6), direct (L1 gather, this file: W % 4 != 0, even-n middle step).  Shapes a kernel
+    // cannot take fall through to the next one.  C = 5 with odd n keeps its chain states in the strip kernel's 4+1
+    // layout; that is decided here, once, because a state written 4+1 must be read 4+1.
+    // (only when frames are emitted: step 1 is then the key-frame variant, the one that reads a planar source)
+    const bool il = (labels || logits) && dense_strip_il_ok(C, H, W, n, prev, next, grids_left[0], grids_right[0], scratch);
     float* Lst = scratch;                       // states 1..n-2
     float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
     for (int j = 1; j <= n - 1; ++j) {
       DenseStep a{};
       a.srcL = (j == 1) ? prev : Lst + (j - 2) * S;
       a.srcR = (j == 1) ? next : Rst + (j - 2) * S;
-      a.gridL = grids_left + static_cast<long long>(j - 1) * HW * 2;
-      a.gridR = grids_right + static_cast<long long>(j - 1) * HW * 2;
+      a.gridL = grids_left[j - 1];
+      a.gridR = grids_right[j - 1];
       a.dstL = (j <= n - 2) ? Lst + (j - 1) * S : nullptr;
       a.dstR = (j <= n - 2) ? Rst + (j - 1) * S : nullptr;
       const bool want_out = labels || logits;
@@ -257,9 +275,9 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
         a.label0 = labels;
         a.logit0 = logits;
       }
-      int r = 1;
-      if (kernel_sel == 0) r = launch_dense_step_strip(a, C, H, W, st);
-      if (r > 0 && kernel_sel <= 1) r = launch_dense_step_tma(a, C, H, W, st);
+      a.il = il ? 1 : 0;
+      int r = launch_dense_step_strip(a, C, H, W, st);
+      if (r > 0) r = launch_dense_step_tma(a, C, H, W, st);
       if (r < 0) return r;
       if (r > 0) {   // not eligible for the TMA-staged kernels: direct-gather kernel
         if (int e = launch_dense_step<Nm>(a, C, H, W, st)) return e;

@@ -66,7 +66,7 @@ class FlowBaseModel(_Base):
                  no_interpolation_percentage: float = 0.0, layers: int = 101, zoom_factor: int = 8,
                  compute_metrics: bool = True, save_images: bool = False, save_video: bool = True,
                  data_root: str = "dataset/flow/", predict_v_id: str = "florida-01", pretrained: bool = True,
-                 backbone: nn.Module | None = None, output_size=(1072, 1920), reuse_keyframes: bool = True,
+                 backbone: nn.Module | None = None, output_size=(1072, 1920), reuse_keyframes: bool = False,
                  **kwargs):
         super().__init__()
         hp = dict(classes=classes, ignore_index=ignore_index, test_h=round_train(test_h, arch),
@@ -260,6 +260,14 @@ class FlowBaseModel(_Base):
         self.last_output = None     # last label map of the previous interval (uint8 [H,W] on device)
         self._predict_intervals = 0
         self.model_G.reset_keyframe_cache()
+        hp = self.hparams
+        if (hp.save_video or hp.save_images) and self.frame_sink is None:
+            # the reference writes an .avi (imageio) / PNGs (PIL) here (flow/base.py:249-253, 297-312): sinks are outside
+            # the accelerated path, so the label maps go to `frame_sink` and nothing is written without one
+            import warnings
+            warnings.warn("FlowBaseModel: save_video / save_images are set but no frame_sink is attached; label maps are "
+                          "returned by predict_step and not written anywhere (set model.frame_sink = callable(frame_id, "
+                          "uint8 ndarray [n,H,W]))", stacklevel=2)
 
     @torch.no_grad()
     def predict_step(self, batch, batch_idx):
@@ -287,24 +295,25 @@ class FlowBaseModel(_Base):
                                             counts=self._predict_counts.counts)
             elif (frame_prev.shape[2], frame_prev.shape[3]) == (out_h, out_w) and not self.model_G.feature_based:
                 # the resize at :275 is an identity copy -> fully fused route
-                fid = int(batch["frame_id"][0]) if "frame_id" in batch else None
+                # the frame id is only needed (and only read: it costs a device-to-host sync when Lightning has moved
+                # the batch to the GPU) for key-frame reuse
+                fid = int(batch["frame_id"][0]) if (self.model_G.reuse_keyframes and "frame_id" in batch) else None
                 output = self.model_G.predict_labels(
                     frame_prev, frame_next, mvs_left, mvs_right, n, prof, tc_prev=self.last_output,
                     counts=self._predict_counts.counts if want_counts else None, ignore_index=hp.ignore_index,
                     frame_id=fid)
             else:
                 logits = self.model_G.predict(frame_prev, frame_next, mvs_left, mvs_right, n, prof)["pred"]
-                logits = kernels.upsample_bilinear_ac(logits, (out_h, out_w))      # flow/base.py:275
-                output = kernels.argmax(logits)                                     # flow/base.py:276
+                output, _ = kernels.upsample_argmax(logits, (out_h, out_w))         # flow/base.py:275-277, one kernel
                 if want_counts:
                     kernels.temporal_counts(output, hp.classes, hp.ignore_index, tc_prev=self.last_output,
                                             counts=self._predict_counts.counts)
             output_numpy = None
-            if self.frame_sink is not None or hp.save_images:
+            if self.frame_sink is not None:
                 output_numpy = output.cpu().numpy()                                 # flow/base.py:277 (already uint8)
         if want_counts:
             steps = output.shape[0] - (1 if self.last_output is None else 0)
-            self._predict_counts.updates += max(steps, 0)
+            self._predict_counts.note_updates(steps)
             self.last_output = output[output.shape[0] - 1]                          # flow/base.py:295
         self._predict_intervals += 1
         if self.frame_sink is not None and output_numpy is not None:

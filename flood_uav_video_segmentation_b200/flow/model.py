@@ -69,11 +69,17 @@ class FlowModel(nn.Module):
         self.no_interpolation_percentage = no_interpolation_percentage
         # Default grid - no motion (plain attribute, not a buffer: flow/model.py:32)
         self.default_motion_vector = torch.from_numpy(get_default_grid()).float().unsqueeze(0)
-        # Key-frame reuse: in the reference every key frame goes through the network twice, as
-        # `next` of interval i and as `prev` of interval i+1 (flow/model.py:189,202).  When the caller passes frame ids
-        # the encoder/decoder output of `next` is kept for the following interval.  Plain attributes, not buffers.
+        # Key-frame reuse (opt-in): in the reference every key frame goes through the network
+        # twice, as `next` of interval i and as `prev` of interval i+1 (flow/model.py:189,202).  When the caller passes
+        # frame ids the network output of `next` is kept for the following interval.  The entry is keyed on everything
+        # that makes it valid — frame id, output size, device, resolution kind, and a version that every change of the
+        # weights or of the mode bumps (train/eval, load_state_dict, .to()/.half()) — and dropped by
+        # reset_keyframe_cache() (FlowBaseModel.on_predict_start: one video per predict run).  Plain attributes.
         self.reuse_keyframes = False
-        self._kf_cache = None          # (frame_id, tensor)
+        self._kf_cache = None          # (key tuple, tensor)
+        self._kf_version = 0
+        # chain-state workspace of the interval kernels, grown on demand and reused across calls
+        self._scratch = kernels.ScratchCache()
 
     # ------------------------------------------------------------------ forward (train / val / test)
     def forward(self, frame_current, frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index):
@@ -178,15 +184,33 @@ class FlowModel(nn.Module):
                 o = _interp_ac(o, h, w)
         return o
 
-    def _cached_keyframe(self, frame_id, shape):
+    def _kf_key(self, frame_id, shape, device, lowres):
+        return (int(frame_id), tuple(shape), str(device), bool(lowres), self._kf_version, bool(self.training))
+
+    def _cached_keyframe(self, frame_id, shape, device, lowres):
         c = self._kf_cache
-        if self.reuse_keyframes and frame_id is not None and c is not None and c[0] == frame_id and \
-                tuple(c[2]) == tuple(shape):
+        if self.reuse_keyframes and frame_id is not None and c is not None and \
+                c[0] == self._kf_key(frame_id, shape, device, lowres):
             return c[1]
         return None
 
     def reset_keyframe_cache(self):
         self._kf_cache = None
+        self._kf_version += 1
+
+    # anything that changes the weights or the mode invalidates cached network outputs
+    def train(self, mode=True):
+        self.reset_keyframe_cache()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.reset_keyframe_cache()
+        self._scratch.clear()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.reset_keyframe_cache()
+        return super().load_state_dict(*args, **kwargs)
 
     def _interval_mode(self, mvs_left, h, w):
         if self.no_warp or len(mvs_left) == 0 or not _is_grid(mvs_left[0]):
@@ -219,8 +243,8 @@ class FlowModel(nn.Module):
         if len(mvs_left) != n - 1 or len(mvs_right) != n - 1:
             raise FuvsError(f"FlowModel.predict: n={n} needs {n - 1} grids per side, got {len(mvs_left)}/{len(mvs_right)}")
         if mode == "dense":
-            return kernels.dense_interval(o, o_next, mvs_left, mvs_right, n, **kw)
-        return kernels.block_interval(o, o_next, mvs_left, mvs_right, n, **kw)
+            return kernels.dense_interval(o, o_next, mvs_left, mvs_right, n, scratch=self._scratch, **kw)
+        return kernels.block_interval(o, o_next, mvs_left, mvs_right, n, scratch=self._scratch, **kw)
 
     def predict_segmentation(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler):
         """flow/model.py:184-241 -> {"pred": [n,C,h,w]} (frame 0 = key-frame logits)."""
@@ -251,12 +275,12 @@ class FlowModel(nn.Module):
         h, w = frame_prev.shape[2], frame_prev.shape[3]
         with torch.no_grad():
             lowres = bool(self.no_warp) and frame_next is not None
-            o = self._cached_keyframe(frame_id, (h, w))
+            o = self._cached_keyframe(frame_id, (h, w), frame_prev.device, lowres)
             if o is None:
                 o = self._keyframe_logits(frame_prev, h, w, profiler, keep_lowres=lowres)
             o_next = self._keyframe_logits(frame_next, h, w, profiler, keep_lowres=lowres) if frame_next is not None else None
             if self.reuse_keyframes and frame_id is not None and o_next is not None:
-                self._kf_cache = (int(frame_id) + int(n), o_next, (h, w))
+                self._kf_cache = (self._kf_key(int(frame_id) + int(n), (h, w), frame_prev.device, lowres), o_next)
             with profiler.profile("predict_warp"):
                 with profiler.profile("predict_fusion"):
                     labels, _ = self._run_interval(o, o_next, mvs_left, mvs_right, n, want_labels=True,
@@ -291,7 +315,8 @@ class FlowModel(nn.Module):
             with profiler.profile("predict_warp"):
                 with profiler.profile("predict_fusion"):
                     feature_maps = kernels.feature_interval(f[0], f_next[0] if f_next is not None else None, mvs_left,
-                                                            mvs_right, frames, default_grid=self.default_motion_vector)
+                                                            mvs_right, frames, default_grid=self.default_motion_vector,
+                                                            scratch=self._scratch)
         else:
             feature_maps = torch.empty((frames, cf, f_h, f_w), dtype=torch.float32, device=dev)
             feature_maps[0].copy_(f[0])

@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import FuvsError, check, load, ptr, require_cuda, stream_ptr
+from ._lib import FuvsError, check, load, ptr, ptr_array, require_cuda, stream_ptr
 
 
 def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
@@ -23,17 +23,55 @@ def new_counts(K: int, device) -> torch.Tensor:
     return torch.zeros((3, K), dtype=torch.int64, device=device)
 
 
-def _stack_grids(mvs, what: str) -> torch.Tensor:
-    """python list of k-1 grids [1,Hg,Wg,2] (or [Hg,Wg,2]) -> fp32 [k-1,Hg,Wg,2].
-
-    FlowModel.warp casts grids with .float() (flow/model.py:246-247)."""
+def _grid_list(mvs, n, shape, dev, what: str):
+    """The reference's grid format — a python list of n-1 tensors [1,Hg,Wg,2] (flow/dataset.py:138-146), or one stacked
+    [n-1,Hg,Wg,2] tensor — as n-1 contiguous fp32 CUDA tensors [Hg,Wg,2] WITHOUT copying: the *_ptrs entries take a
+    host array of device pointers.  Only what the reference itself converts is converted (FlowModel.warp casts
+    non-float grids with .float(), flow/model.py:246-247); a non-contiguous grid is made contiguous."""
     if isinstance(mvs, torch.Tensor):
-        g = mvs
-    else:
-        g = torch.stack([m.reshape(m.shape[-3], m.shape[-2], 2) for m in mvs], 0)
-    if g.dtype != torch.float32:
-        g = g.float()
-    return g.contiguous()
+        mvs = [mvs[j] for j in range(mvs.shape[0])]
+    if len(mvs) != n - 1:
+        raise FuvsError(f"{what}: n={n} needs {n - 1} grids per side, got {len(mvs)}")
+    out = []
+    for m in mvs:
+        if not isinstance(m, torch.Tensor) or m.dim() < 3 or m.shape[-1] != 2:
+            raise FuvsError(f"{what}: a grid must be a tensor [..,Hg,Wg,2], got {getattr(m, 'shape', type(m))}")
+        g = m.reshape(m.shape[-3], m.shape[-2], 2)
+        if shape is not None and tuple(g.shape[:2]) != tuple(shape):
+            raise FuvsError(f"{what}: grids must be [{shape[0]},{shape[1]},2], got {tuple(g.shape)}")
+        if g.dtype != torch.float32:
+            g = g.float()
+        if not g.is_contiguous():
+            g = g.contiguous()
+        out.append(g)
+    require_cuda(*out, what=what)
+    if out and out[0].device != dev:
+        raise FuvsError(f"{what}: grids on {out[0].device}, key frames on {dev}")
+    return out
+
+
+class ScratchCache:
+    """Per-owner workspace for the interval entries (chain states): grown on demand, reused across calls, so that an
+    evaluation loop does not allocate 249 MB per dense interval.  Owned by the caller (FlowModel keeps one)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, floats: int, dev) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < floats or self.buf.device != dev:
+            self.buf = torch.empty((max(int(floats), 1),), dtype=torch.float32, device=dev)
+        return self.buf
+
+    def clear(self):
+        self.buf = None
+
+
+def _scratch(scratch, need, dev):
+    if isinstance(scratch, ScratchCache):
+        return scratch.get(need, dev)
+    if scratch is None or scratch.numel() < need:
+        return torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+    return scratch
 
 
 def linear_blend_argmax(prev, nxt, n, *, want_labels=True, want_logits=False, tc_prev=None, counts=None,
@@ -116,33 +154,30 @@ def warp_step(src0, grid0, src1=None, grid1=None, *, align_corners=False):
 
 def dense_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, want_logits=False, tc_prev=None,
                    counts=None, ignore_index=255, scratch=None):
-    """fuvs_dense_interval.  grids_*: list of n-1 [1,H,W,2] tensors or a stacked [n-1,H,W,2]."""
+    """fuvs_dense_interval_ptrs.  grids_*: list of n-1 [1,H,W,2] tensors (the reference's format, passed as a pointer
+    table: nothing is stacked) or a stacked [n-1,H,W,2].  scratch: tensor, ScratchCache or None (allocated per call)."""
     dev = require_cuda(prev, nxt, tc_prev, counts, what="dense_interval")
     prev = _f32c(prev, "prev")
     C, H, W = prev.shape[-3:]
     gl = gr = None
     if n > 1:
         nxt = _f32c(nxt, "next")
-        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
-        require_cuda(gl, gr, what="dense_interval(grids)")
-        if tuple(gl.shape) != (n - 1, H, W, 2) or tuple(gr.shape) != (n - 1, H, W, 2):
-            raise FuvsError(f"dense_interval: grids must be [{n - 1},{H},{W},2], got {tuple(gl.shape)} / {tuple(gr.shape)}")
-    need = int(load().fuvs_dense_scratch_floats(C, H, W, n))
-    if scratch is None or scratch.numel() < need:
-        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+        gl = _grid_list(grids_left, n, (H, W), dev, "dense_interval(grids_left)")
+        gr = _grid_list(grids_right, n, (H, W), dev, "dense_interval(grids_right)")
+    scratch = _scratch(scratch, int(load().fuvs_dense_scratch_floats(C, H, W, n)), dev)
     labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
     logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
     _check_tc(tc_prev, counts, H, W, C)
     with torch.cuda.device(dev):
-        check(load().fuvs_dense_interval(ptr(prev), ptr(nxt) if n > 1 else None, ptr(gl), ptr(gr), C, H, W, n,
-                                         ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
-                                         ignore_index, stream_ptr(dev)))
+        check(load().fuvs_dense_interval_ptrs(ptr(prev), ptr(nxt) if n > 1 else None, ptr_array(gl), ptr_array(gr), C, H, W,
+                                              n, ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
+                                              ignore_index, stream_ptr(dev)))
     return labels, logits
 
 
 def block_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, want_logits=False, tc_prev=None,
                    counts=None, ignore_index=255, scratch=None):
-    """fuvs_block_interval.  grids_*: list of n-1 [1,Hg,Wg,2] tensors or stacked [n-1,Hg,Wg,2]."""
+    """fuvs_block_interval_ptrs.  grids_*: list of n-1 [1,Hg,Wg,2] tensors or stacked [n-1,Hg,Wg,2]."""
     dev = require_cuda(prev, nxt, tc_prev, counts, what="block_interval")
     prev = _f32c(prev, "prev")
     C, H, W = prev.shape[-3:]
@@ -150,21 +185,51 @@ def block_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, w
     Hg = Wg = 0
     if n > 1:
         nxt = _f32c(nxt, "next")
-        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
-        require_cuda(gl, gr, what="block_interval(grids)")
-        Hg, Wg = gl.shape[1:3]
-        if tuple(gl.shape) != (n - 1, Hg, Wg, 2) or tuple(gr.shape) != tuple(gl.shape):
-            raise FuvsError(f"block_interval: grids must both be [{n - 1},Hg,Wg,2], got {tuple(gl.shape)} / {tuple(gr.shape)}")
-    need = int(load().fuvs_block_scratch_floats(C, Hg, Wg, n))
-    if scratch is None or scratch.numel() < need:
-        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+        gl = _grid_list(grids_left, n, None, dev, "block_interval(grids_left)")
+        Hg, Wg = gl[0].shape[:2]
+        gl = _grid_list(gl, n, (Hg, Wg), dev, "block_interval(grids_left)")
+        gr = _grid_list(grids_right, n, (Hg, Wg), dev, "block_interval(grids_right)")
+    scratch = _scratch(scratch, int(load().fuvs_block_scratch_floats(C, Hg, Wg, n)), dev)
     labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
     logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
     _check_tc(tc_prev, counts, H, W, C)
     with torch.cuda.device(dev):
-        check(load().fuvs_block_interval(ptr(prev), ptr(nxt) if n > 1 else None, ptr(gl), ptr(gr), C, H, W, Hg, Wg, n,
-                                         ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
-                                         ignore_index, stream_ptr(dev)))
+        check(load().fuvs_block_interval_ptrs(ptr(prev), ptr(nxt) if n > 1 else None, ptr_array(gl), ptr_array(gr), C, H, W,
+                                              Hg, Wg, n, ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts),
+                                              ignore_index, stream_ptr(dev)))
+    return labels, logits
+
+
+def block_clip(keys, grids_left, grids_right, n, *, want_logits=False, tc_prev=None, counts=None, ignore_index=255,
+               scratch=None):
+    """fuvs_block_clip: m consecutive intervals of one clip in one call.  keys: m+1 key-frame logit maps [1,C,H,W] /
+    [C,H,W]; grids_left / grids_right: per interval a list of n-1 grids.  Returns (labels [m,n,H,W] uint8, logits
+    [m,n,C,H,W] or None); interval i's frame 0 is counted against the last map of interval i-1 (tc_prev for i = 0)."""
+    m = len(keys) - 1
+    if m < 1 or len(grids_left) != m or len(grids_right) != m:
+        raise FuvsError(f"block_clip: {len(keys)} key frames need {len(keys) - 1} grid lists per side")
+    dev = require_cuda(*keys, tc_prev, counts, what="block_clip")
+    keys = [_f32c(k, "key frame") for k in keys]
+    C, H, W = keys[0].shape[-3:]
+    if any(tuple(k.shape[-3:]) != (C, H, W) for k in keys):
+        raise FuvsError("block_clip: key frames differ in shape")
+    gl, gr = [], []
+    Hg = Wg = 0
+    if n > 1:
+        first = _grid_list(grids_left[0], n, None, dev, "block_clip(grids_left)")
+        Hg, Wg = first[0].shape[:2]
+        for i in range(m):
+            gl += _grid_list(grids_left[i], n, (Hg, Wg), dev, "block_clip(grids_left)")
+            gr += _grid_list(grids_right[i], n, (Hg, Wg), dev, "block_clip(grids_right)")
+    scratch = _scratch(scratch, m * int(load().fuvs_block_scratch_floats(C, Hg, Wg, n)), dev)
+    labels = torch.empty((m, n, H, W), dtype=torch.uint8, device=dev)
+    logits = torch.empty((m, n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_block_clip(m, ptr_array(keys), ptr_array(gl) if n > 1 else None, ptr_array(gr) if n > 1 else None,
+                                     C, H, W, Hg, Wg, n, ptr(scratch), ptr_array([labels[i] for i in range(m)]),
+                                     ptr_array([logits[i] for i in range(m)]) if want_logits else None, ptr(tc_prev),
+                                     ptr(counts), ignore_index, stream_ptr(dev)))
     return labels, logits
 
 
@@ -185,6 +250,23 @@ def upsample_bilinear_ac(src, size, out=None):
     with torch.cuda.device(dev):
         check(load().fuvs_upsample_bilinear_ac(ptr(src), ptr(out), planes, Hin, Win, Hout, Wout, stream_ptr(dev)))
     return out
+
+
+def upsample_argmax(logits, size, *, want_resized=False):
+    """fuvs_upsample_argmax: F.interpolate(logits, size, bilinear, align_corners=True).max(1)[1] as uint8 (flow/base.py:
+    275-277) -> (labels [F,Hout,Wout], resized logits or None)."""
+    dev = require_cuda(logits, what="upsample_argmax")
+    logits = _f32c(logits, "logits")
+    if logits.dim() != 4:
+        raise FuvsError("upsample_argmax: expected [F,C,H,W]")
+    F_, Cc, Hin, Win = logits.shape
+    Hout, Wout = int(size[0]), int(size[1])
+    labels = torch.empty((F_, Hout, Wout), dtype=torch.uint8, device=dev)
+    resized = torch.empty((F_, Cc, Hout, Wout), dtype=torch.float32, device=dev) if want_resized else None
+    with torch.cuda.device(dev):
+        check(load().fuvs_upsample_argmax(ptr(logits), F_, Cc, Hin, Win, Hout, Wout, ptr(labels), ptr(resized),
+                                          stream_ptr(dev)))
+    return labels, resized
 
 
 def blend_argmax(a, b, wa, wb, *, want_out=True, want_labels=False, out=None):
@@ -317,23 +399,20 @@ def feature_interval(f_prev, f_next, grids_left, grids_right, n, *, default_grid
     Hg = Wg = 0
     if n > 1:
         f_next = _f32c(f_next, "f_next")
-        gl, gr = _stack_grids(grids_left, "grids_left"), _stack_grids(grids_right, "grids_right")
-        require_cuda(gl, gr, what="feature_interval(grids)")
-        Hg, Wg = gl.shape[1:3]
-        if tuple(gl.shape) != (n - 1, Hg, Wg, 2) or tuple(gr.shape) != tuple(gl.shape):
-            raise FuvsError("feature_interval: grids must both be [n-1,Hg,Wg,2]")
+        gl = _grid_list(grids_left, n, None, dev, "feature_interval(grids_left)")
+        Hg, Wg = gl[0].shape[:2]
+        gl = _grid_list(gl, n, (Hg, Wg), dev, "feature_interval(grids_left)")
+        gr = _grid_list(grids_right, n, (Hg, Wg), dev, "feature_interval(grids_right)")
     Hd = Wd = 0
     if default_grid is not None:
         default_grid = _f32c(default_grid if default_grid.dtype == torch.float32 else default_grid.float(), "default_grid")
         Hd, Wd = default_grid.shape[-3:-1]
-    need = int(load().fuvs_feature_scratch_floats(C, Hg, Wg, Hd, Wd, n))
-    if scratch is None or scratch.numel() < need:
-        scratch = torch.empty((max(need, 1),), dtype=torch.float32, device=dev)
+    scratch = _scratch(scratch, int(load().fuvs_feature_scratch_floats(C, Hg, Wg, Hd, Wd, n)), dev)
     if out is None:
         out = torch.empty((n, C, fh, fw), dtype=torch.float32, device=dev)
     elif tuple(out.shape) != (n, C, fh, fw) or out.dtype != torch.float32 or not out.is_contiguous():
         raise FuvsError("feature_interval: bad `out` tensor")
     with torch.cuda.device(dev):
-        check(load().fuvs_feature_interval(ptr(f_prev), ptr(f_next) if n > 1 else None, ptr(gl), ptr(gr), ptr(default_grid),
+        check(load().fuvs_feature_interval_ptrs(ptr(f_prev), ptr(f_next) if n > 1 else None, ptr_array(gl), ptr_array(gr), ptr(default_grid),
                                            Hd, Wd, C, fh, fw, Hg, Wg, n, ptr(scratch), ptr(out), stream_ptr(dev)))
     return out

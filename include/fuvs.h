@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define FUVS_ABI_VERSION 1
+#define FUVS_ABI_VERSION 2
 
 /* error codes */
 #define FUVS_OK        0
@@ -151,6 +151,16 @@ FUVS_API int fuvs_dense_interval(const float* prev, const float* next,
                         uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts,
                         int ignore_index, fuvs_stream_t stream);
+/* The same with the grids in the reference's own format: the python LISTS mvs_left / mvs_right of n-1 separate
+ * [1,H,W,2] tensors (flow/dataset.py:138-146) arrive as HOST arrays of n-1 DEVICE pointers, read during the call;
+ * nothing is stacked or copied.  (The layout of `scratch` is private to the library.) */
+FUVS_API int fuvs_dense_interval_ptrs(const float* prev, const float* next,
+                        const float* const* grids_left_host, const float* const* grids_right_host,
+                        int C, int H, int W, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Macro-block-grid interval (reference-faithful: grids are [Hg,Wg,2] with
@@ -176,6 +186,29 @@ FUVS_API int fuvs_block_interval(const float* prev, const float* next,
                         uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts,
                         int ignore_index, fuvs_stream_t stream);
+/* grids as host arrays of n-1 device pointers (the list format of flow/dataset.py:138-146), see
+ * fuvs_dense_interval_ptrs */
+FUVS_API int fuvs_block_interval_ptrs(const float* prev, const float* next,
+                        const float* const* grids_left_host, const float* const* grids_right_host,
+                        int C, int H, int W, int Hg, int Wg, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
+/* m CONSECUTIVE intervals of one clip in one call (what m successive predict_step calls compute, flow/base.py:259-295):
+ * interval i lies between keys_host[i] and keys_host[i+1] (m+1 key-frame logit maps), uses the grids
+ * grids_*_host[i*(n-1) .. i*(n-1)+n-2], writes labels_host[i] ([n,H,W]) and logits_host[i] (or NULL arrays), and its
+ * frame 0 is compared with the last label map of interval i-1 (tc_prev for i = 0).  The chains of a clip's intervals
+ * do not depend on each other, so each of the n-1 dependent chain steps is ONE launch for all m intervals: the launch
+ * latencies that dominate a single block-grid interval are paid once per clip.
+ *   scratch : m * fuvs_block_scratch_floats(C,Hg,Wg,n) floats;  all *_host arguments are host arrays of device pointers */
+FUVS_API int fuvs_block_clip(int m, const float* const* keys_host,
+                        const float* const* grids_left_host, const float* const* grids_right_host,
+                        int C, int H, int W, int Hg, int Wg, int n,
+                        float* scratch,
+                        uint8_t* const* labels_host, float* const* logits_host,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Feature-level interval (model.feature_based=True) — FlowModel.predict_feature,
@@ -194,6 +227,12 @@ FUVS_API int fuvs_block_interval(const float* prev, const float* next,
 FUVS_API long long fuvs_feature_scratch_floats(int C, int Hg, int Wg, int Hd, int Wd, int n);
 FUVS_API int fuvs_feature_interval(const float* f_prev, const float* f_next,
                           const float* grids_left, const float* grids_right,
+                          const float* default_grid, int Hd, int Wd,
+                          int C, int fh, int fw, int Hg, int Wg, int n,
+                          float* scratch, float* out, fuvs_stream_t stream);
+/* grids as host arrays of n-1 device pointers, see fuvs_dense_interval_ptrs */
+FUVS_API int fuvs_feature_interval_ptrs(const float* f_prev, const float* f_next,
+                          const float* const* grids_left_host, const float* const* grids_right_host,
                           const float* default_grid, int Hd, int Wd,
                           int C, int fh, int fw, int Hg, int Wg, int n,
                           float* scratch, float* out, fuvs_stream_t stream);
@@ -226,6 +265,16 @@ FUVS_API int fuvs_blend_argmax(const float* a, const float* b, double wa, double
 FUVS_API int fuvs_argmax(const float* logits, int frames, int C, long long HW,
                 uint8_t* labels_u8, long long* labels_i64,
                 fuvs_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * predict_step's final resize, fused with the arg-max — flow/base.py:275-277:
+ *   output = F.interpolate(output, (1072, 1920), mode='bilinear', align_corners=True)
+ *   output = output.data.max(1)[1]            (+ the uint8 cast of :277)
+ * logits [frames,C,Hin,Win] -> labels [frames,Hout,Wout] uint8; the resized logits are only written when `resized`
+ * ([frames,C,Hout,Wout]) is not NULL.  Hin==Hout && Win==Wout is the copy ATen makes, i.e. a plain arg-max.
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_upsample_argmax(const float* logits, int frames, int C, int Hin, int Win, int Hout, int Wout,
+                         uint8_t* labels, float* resized, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * intersectionAndUnionGPU / intersectionAndUnion — util/util.py:52-63, 36-47.

@@ -7,7 +7,7 @@ from torch import nn
 
 from flood_uav_video_segmentation_b200 import kernels
 from flood_uav_video_segmentation_b200.base.foundation import compute_metrics, epoch_metrics
-from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel
+from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel, SimpleProfiler
 from flood_uav_video_segmentation_b200.flow.model import FlowModel
 from flood_uav_video_segmentation_b200.synthetic import flow_grids, gt_labels
 from oracle import flow_oracle as fo
@@ -252,3 +252,37 @@ def test_keyframe_reuse_gives_identical_labels(cuda):
     for a, b in zip(results[False][0], results[True][0]):
         assert torch.equal(a, b)
     assert np.array_equal(results[False][1], results[True][1])
+
+
+def test_keyframe_cache_is_invalidated_by_weight_and_mode_changes(cuda):
+    """The opt-in key-frame cache must never hand back logits of other weights, another mode, another device or
+    another size: every such change bumps the cache version."""
+    H, W, n, C = 64, 96, 3, 5
+    bb = TinyBackbone(classes=C).to(cuda).eval()
+    fm = FlowModel(bb, feature_based=False, no_warp=True).to(cuda).eval()
+    fm.reuse_keyframes = True
+    prof = SimpleProfiler()
+    x0, x1 = torch.randn(1, 3, H, W, device=cuda), torch.randn(1, 3, H, W, device=cuda)
+    dummy = [torch.zeros(1, 1, device=cuda)] * (n - 1)
+    fm.predict_labels(x0, x1, dummy, dummy, n, prof, frame_id=0)
+    assert fm._kf_cache is not None and fm._cached_keyframe(n, (H, W), x0.device, True) is not None
+    assert fm._cached_keyframe(n, (H + 8, W), x0.device, True) is None          # another size
+    assert fm._cached_keyframe(n, (H, W), x0.device, False) is None             # full-resolution vs decoder-resolution
+    for change in (lambda: fm.train(), lambda: fm.eval(), lambda: fm.load_state_dict(fm.state_dict()),
+                   lambda: fm.float(), lambda: fm.reset_keyframe_cache()):
+        fm.eval()
+        fm.predict_labels(x0, x1, dummy, dummy, n, prof, frame_id=0)
+        assert fm._cached_keyframe(n, (H, W), x0.device, True) is not None
+        change()
+        assert fm._cached_keyframe(n, (H, W), x0.device, True) is None
+    # and with new weights the second interval really uses them
+    fm.eval()
+    a = fm.predict_labels(x1, x0, dummy, dummy, n, prof, frame_id=n)
+    with torch.no_grad():
+        for p in bb.parameters():
+            p.mul_(-1.0)
+    fm.load_state_dict(fm.state_dict())
+    b = fm.predict_labels(x1, x0, dummy, dummy, n, prof, frame_id=n)
+    fm.reuse_keyframes = False
+    c = fm.predict_labels(x1, x0, dummy, dummy, n, prof)
+    assert torch.equal(b, c) and not torch.equal(a, b)

@@ -502,3 +502,76 @@ def test_limits_and_degenerate_shapes(cuda):
     # empty metric input: nothing is counted, nothing fails
     counts = kernels.confusion(torch.zeros(0, dtype=torch.uint8, device=cuda), torch.zeros(0, dtype=torch.int64, device=cuda), 5)
     assert int(counts.sum()) == 0
+
+
+@pytest.mark.parametrize("C,H,W,n,m", [(5, 272, 480, 5, 3), (2, 64, 96, 4, 2), (5, 37, 53, 3, 4), (5, 48, 64, 1, 2),
+                                       (6, 48, 64, 5, 9)])
+def test_block_clip(cuda, C, H, W, n, m):
+    """fuvs_block_clip (m consecutive intervals, chain steps batched over the clip) against m successive
+    fuvs_block_interval calls and against the oracle: labels, logits and the chained temporal counts bit-exact."""
+    keys = [keyframe_logits(C, H, W, 4, j)[None].to(cuda) for j in range(m + 1)]
+    gl = [[g.to(cuda) for g in flow_grids(H, W, n, "block", clip=4, interval=i, side=0)] for i in range(m)]
+    gr = [[g.to(cuda) for g in flow_grids(H, W, n, "block", clip=4, interval=i, side=1)] for i in range(m)]
+    tc0 = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(3), dtype=torch.uint8).to(cuda)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.block_clip(keys, gl, gr, n, want_logits=True, tc_prev=tc0, counts=counts)
+    assert tuple(labels.shape) == (m, n, H, W) and tuple(logits.shape) == (m, n, C, H, W)
+    counts_ref = kernels.new_counts(C, cuda)
+    ref_counts = np.zeros((3, C), np.int64)
+    last, last_np = tc0, tc0.cpu().numpy().astype(np.int64)
+    for i in range(m):
+        li, gi = kernels.block_interval(keys[i], keys[i + 1] if n > 1 else None, gl[i], gr[i], n, want_labels=True,
+                                        want_logits=True, tc_prev=last, counts=counts_ref)
+        assert torch.equal(labels[i], li), f"interval {i}: labels differ from the per-interval entry"
+        assert bits_equal(logits[i], gi), f"interval {i}: logits differ from the per-interval entry"
+        ref_logits, ref_labels = oracle_interval(keys[i], keys[i + 1] if n > 1 else keys[i], gl[i], gr[i], n, False, cuda)
+        if n == 1:
+            ref_logits, ref_labels = keys[i], fo.argmax_labels(keys[i])
+        assert bits_equal(logits[i], ref_logits), f"interval {i}: logits differ from the oracle"
+        assert torch.equal(labels[i].long(), ref_labels)
+        c, last_np = oracle_temporal(ref_labels, C, last_np)
+        ref_counts += c
+        last = li[n - 1]
+    assert torch.equal(counts, counts_ref)
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+
+
+@pytest.mark.parametrize("F_,C,Hin,Win,Hout,Wout", [(5, 5, 1080, 1920, 1072, 1920), (2, 5, 433, 433, 1072, 1920),
+                                                     (3, 2, 37, 53, 41, 59), (1, 7, 17, 25, 136, 201),
+                                                     (2, 5, 48, 64, 48, 64), (1, 3, 1, 1, 5, 7)])
+def test_upsample_argmax(cuda, F_, C, Hin, Win, Hout, Wout):
+    """fuvs_upsample_argmax = predict_step's F.interpolate(.., (1072,1920), bilinear, align_corners=True) + max(1)[1] +
+    uint8 (flow/base.py:275-277) in one kernel: labels and (optional) resized logits bit-exact against torch-CUDA."""
+    g = torch.Generator().manual_seed(F_ * 100 + Hin)
+    x = (torch.randn(F_, C, Hin, Win, generator=g) * 2).to(cuda)
+    x[0, :, 0, 0] = 0.5            # a tie: the lowest class index must win
+    if Hin > 2 and Win > 2:
+        x[0, 1, 1, 1] = float("nan")
+        x[0, C - 1, 2, 1] = float("inf")
+    ref = F.interpolate(x, size=(Hout, Wout), mode="bilinear", align_corners=True)
+    labels, resized = kernels.upsample_argmax(x, (Hout, Wout), want_resized=True)
+    assert bits_equal(resized, ref)
+    assert torch.equal(labels.long(), ref.max(1)[1])
+    labels2, none = kernels.upsample_argmax(x, (Hout, Wout))
+    assert none is None and torch.equal(labels2, labels)
+
+
+def test_grid_lists_are_passed_by_pointer(cuda):
+    """The reference hands the grids as a python list of separate tensors (flow/dataset.py:138-146): the interval entries
+    take them as a pointer table, so grids living in unrelated allocations (and views at odd offsets of a bigger
+    buffer) give the same result as one stacked tensor."""
+    C, H, W, n = 5, 64, 96, 5
+    o, o_next = keyframe_logits(C, H, W, 6, 0)[None].to(cuda), keyframe_logits(C, H, W, 6, 1)[None].to(cuda)
+    for mode, fn in (("dense", kernels.dense_interval), ("block", kernels.block_interval)):
+        gl = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=6, side=0)]
+        gr = [g.to(cuda) for g in flow_grids(H, W, n, mode, clip=6, side=1)]
+        big = torch.zeros(gl[0].numel() * 2 * n + 64, device=cuda)
+        views = []
+        for j, gsrc in enumerate(gl):                      # scattered views, 8-byte aligned, in reverse order
+            off = (n - 2 - j) * 2 * gsrc.numel() + 2 * j
+            v = big[off:off + gsrc.numel()].view(gsrc.shape)
+            v.copy_(gsrc)
+            views.append(v)
+        a = fn(o, o_next, torch.cat(gl, 0), torch.cat(gr, 0), n, want_logits=True)
+        b = fn(o, o_next, views, gr, n, want_logits=True)
+        assert torch.equal(a[0], b[0]) and bits_equal(a[1], b[1]), mode
