@@ -18,8 +18,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = kernels.load()
 clips = [bench.make_clip(mode, dev, i) for i in range(4)]
-need = max(int(lib.fuvs_dense_scratch_floats(bench.C, bench.H, bench.W, bench.K_DELTA)),
-           int(lib.fuvs_block_scratch_floats(bench.C, bench.H // 16, bench.W // 16, bench.K_DELTA)), 1)
+need = max(bench.scratch_floats(kernels, mode), 1)
 scratch = [torch.empty((need,), dtype=torch.float32, device=dev) for _ in range(S)]
 counts = [kernels.new_counts(bench.C, dev) for _ in range(S)]
 streams = [torch.cuda.Stream(dev) for _ in range(S)]
@@ -34,8 +33,7 @@ def step():
     for c, clip in enumerate(clips):
         s = c % S
         with torch.cuda.stream(streams[s]):
-            bench.run_interval.scratch = scratch[s]
-            bench.run_clip(kernels, mode, clip, counts[s])
+            bench.run_clip(kernels, mode, clip, counts[s], scratch[s])
     for s in range(S):
         e = torch.cuda.Event()
         e.record(streams[s])
@@ -61,5 +59,5 @@ with torch.cuda.stream(side):
     torch.cuda.synchronize(dev)
 ms = e0.elapsed_time(e1)
 iv = steps * len(clips) * 3
-print(f"{mode} streams={S} PDL={os.environ.get('FUVS_STRIP_PDL', '1')} TROWS={os.environ.get('FUVS_STRIP_TROWS', '4')}: "
+print(f"{mode} streams={S}: "
       f"{ms * 1e3 / iv:.2f} us/interval, frac {bench.algorithmic_bytes(mode) * iv / (ms / 1e3) / 1e9 / 6548.8:.4f}")

@@ -17,12 +17,9 @@ a = ap.parse_args()
 dev = torch.device("cuda", 0)
 clips = [bench.make_clip(a.mode, dev, i) for i in range(a.clips)]
 counts = kernels.new_counts(bench.C, dev)
-lib = kernels.load()
-need = max(int(lib.fuvs_dense_scratch_floats(bench.C, bench.H, bench.W, bench.K_DELTA)),
-           int(lib.fuvs_block_scratch_floats(bench.C, bench.H // 16, bench.W // 16, bench.K_DELTA)), 1)
-bench.run_interval.scratch = torch.empty((need,), dtype=torch.float32, device=dev)
+scratch = torch.empty((max(bench.scratch_floats(kernels, a.mode), 1),), dtype=torch.float32, device=dev)
 for _ in range(a.reps):
     for c in clips:
-        bench.run_clip(kernels, a.mode, c, counts)
+        bench.run_clip(kernels, a.mode, c, counts, scratch)
 torch.cuda.synchronize()
 print("ok", counts.sum().item())
