@@ -1,4 +1,5 @@
 """CPU tier: host-side logic of the drop-in layer (no kernels are launched)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -106,3 +107,44 @@ def test_training_route_matches_oracle_on_cpu():
     assert torch.equal(out, ref) and out.requires_grad
     out.sum().backward()
     assert bb.encoder.weight.grad is not None
+
+
+def test_gridpack_matches_the_reference_dataset_loading(tmp_path):
+    """GridPack against the reference's own loading logic, restated from flow/dataset.py:138-146,
+    231-240: per-frame float64 .npy files -> np.load(..).astype('float32') -> mvs_left in order, mvs_right reversed."""
+    import numpy as np
+    import torch
+    from flood_uav_video_segmentation_b200.flow.gridpack import GridPack
+    root, v_id, k = str(tmp_path), "florida-01", 5
+    rng = np.random.default_rng(0)
+    for name in ("grids", "inv_grids"):
+        os.makedirs(os.path.join(root, "frames", v_id, name))
+    ids = list(range(3, 20))
+    for i in ids:
+        for name in ("grids", "inv_grids"):
+            np.save(os.path.join(root, "frames", v_id, name, f"{i}.npy"), rng.uniform(-1, 1, (67, 120, 2)))   # float64 like the reference
+    np.save(os.path.join(root, "frames", v_id, "grids", "40.npy"), np.zeros((67, 120, 2)))                     # a gap: not part of the run
+
+    def ref_load(i, name):                       # flow/dataset.py:239-240
+        return np.load(os.path.join(root, "frames", v_id, name, f"{i}.npy")).astype("float32")
+
+    pack = GridPack.from_directory(root, v_id)
+    assert len(pack) == len(ids) and pack.first_id == 3 and pack.grids.dtype == torch.float32
+    for f_index in (3, 7, 14):
+        left, right = pack.interval(f_index, k)
+        ref_left = [ref_load(f_index + i + 1, "grids") for i in range(k - 1)]                                  # :140-141
+        ref_right = [ref_load(f_index + i + 1, "inv_grids") for i in range(k - 1)]                             # :143-144
+        ref_right.reverse()                                                                                   # :146
+        assert len(left) == len(right) == k - 1
+        for a, b in zip(left, ref_left):
+            assert tuple(a.shape) == (1, 67, 120, 2) and np.array_equal(a[0].numpy(), b)
+        for a, b in zip(right, ref_right):
+            assert np.array_equal(a[0].numpy(), b)
+        l2, r2 = pack.interval_to("cpu", f_index, k)
+        assert all(torch.equal(a, b) for a, b in zip(l2, left)) and all(torch.equal(a, b) for a, b in zip(r2, right))
+    with pytest.raises(IndexError):
+        pack.interval(16, k)
+    p = os.path.join(root, "pack.pt")
+    pack.save(p)
+    again = GridPack.load(p)
+    assert torch.equal(again.grids, pack.grids) and torch.equal(again.inv_grids, pack.inv_grids) and again.first_id == 3
