@@ -54,6 +54,9 @@ def algorithmic_bytes(mode, k=K_DELTA):
     if mode in ("block", "block_clip"):
         hg, wg = H // 16, W // 16
         return S_BYTES + 8 * C * hg * wg * 4 + 2 * (k - 1) * hg * wg * 8 + (k + 1) * LB_BYTES
+    if mode == "block_lowres":     # key frames at decoder resolution: frame 0 and the first chain step up-sample on the fly
+        hg, wg = H // 16, W // 16
+        return 2 * C * (H // 8) * (W // 8) * 4 + 8 * C * hg * wg * 4 + 2 * (k - 1) * hg * wg * 8 + (k + 1) * LB_BYTES
     g = H * W * 8
     return (5 * k - (8 if k % 2 == 0 else 7)) * S_BYTES + 2 * (k - 1) * g + (k + 1) * LB_BYTES
 
@@ -124,10 +127,11 @@ def make_grids(n_grids, mode, device, gen):
 def make_clip(mode, device, seed):
     """One 16-frame clip: 4 key-frame logit maps [1,C,H,W] and, per interval, stacked grids [k-1,Hg,Wg,2] x2."""
     gen = torch.Generator(device=device).manual_seed(seed)
-    if mode == "block_clip":       # same inputs as "block": only the entry point differs
+    lowres = mode in ("linear_lowres", "block_lowres")
+    if mode in ("block_clip", "block_lowres"):       # same grids as "block": only the entry point / key-frame size differ
         mode = "block"
     n_int = (CLIP_FRAMES - 1) // K_DELTA
-    kh, kw = (H // 8, W // 8) if mode == "linear_lowres" else (H, W)
+    kh, kw = (H // 8, W // 8) if lowres else (H, W)
     keys = [torch.randn((1, C, kh, kw), device=device, generator=gen) for _ in range(n_int + 1)]
     grids = []
     for _ in range(n_int):
@@ -207,6 +211,9 @@ def run_interval(kernels, mode, keys, grids, it, tc_prev, counts, scratch=None):
     elif mode in ("dense", "dense_smooth"):
         labels, _ = kernels.dense_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
                                            counts=counts, scratch=scratch)
+    elif mode == "block_lowres":
+        labels, _ = kernels.block_lowres_interval(keys[it], keys[it + 1], (H, W), grids[it][0], grids[it][1], K_DELTA,
+                                                  tc_prev=tc_prev, counts=counts, scratch=scratch)
     else:
         labels, _ = kernels.block_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
                                            counts=counts, scratch=scratch)
@@ -230,7 +237,7 @@ def scratch_floats(kernels, mode):
     lib = kernels.load()
     if mode in ("dense", "dense_smooth"):
         return int(lib.fuvs_dense_scratch_floats(C, H, W, K_DELTA))
-    if mode in ("block", "block_clip"):
+    if mode in ("block", "block_clip", "block_lowres"):
         return 3 * int(lib.fuvs_block_scratch_floats(C, H // 16, W // 16, K_DELTA))
     return 1
 
@@ -783,7 +790,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="dense", choices=["dense", "block", "block_clip", "linear", "dense_smooth", "linear_lowres"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "block", "block_clip", "block_lowres", "linear", "dense_smooth", "linear_lowres"])
     ap.add_argument("--clips-per-step", type=int, default=36, help="36 clips = 108 intervals: a dense step is ~25 ms")
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent clips of a step alternate over")
@@ -857,7 +864,7 @@ def main():
         out["single_stream"] = {"us_per_interval": ms1 * 1e3 / iv1, "achieved_gbs": a1, "frac": a1 / peak,
                                 "value": iv1 * (K_DELTA - 1) * world / (ms1 / 1e3), "unit": "frames/s"}
 
-    if rank == 0 and world == 1 and not args.no_cpu and mode != "linear_lowres":
+    if rank == 0 and world == 1 and not args.no_cpu and mode not in ("linear_lowres", "block_lowres"):
         # the reference's own op sequence as stock torch-CUDA kernels on the same GPU, inputs resident (context for
         # `value`: there is no Blackwell-specific reference kernel to compare with)
         n_st = 6
@@ -922,7 +929,7 @@ def main():
             del mclips
             torch.cuda.empty_cache()
 
-        for m in ("linear", "linear_lowres", "block", "block_clip", "dense", "dense_smooth"):
+        for m in ("linear", "linear_lowres", "block", "block_clip", "block_lowres", "dense", "dense_smooth"):
             if m != mode:
                 measure(m, m, False, m in ("linear", "block", "dense_smooth"))
         # BASELINE.json configs[0]: data.train_w = 433 crops, beside the reference's CPU path

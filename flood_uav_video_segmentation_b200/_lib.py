@@ -43,6 +43,8 @@ SIGNATURES = {
     "fuvs_block_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_block_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_interval_ptrs": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_block_lowres_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "fuvs_block_lowres_interval_ptrs": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_clip": (_i, [_i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_feature_scratch_floats": (_ll, [_i, _i, _i, _i, _i, _i]),
     "fuvs_feature_interval": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

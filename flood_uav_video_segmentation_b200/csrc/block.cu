@@ -21,7 +21,7 @@ namespace fuvs {
 
 int launch_block_stream_rows(const float* key0, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
                              int n, float sh, float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev,
-                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st);
+                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl);
 int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
                            int ignore_index, long long* counts, cudaStream_t st);
 int launch_argmax(const float* logits, int frames, int C, long long HW, uint8_t* u8, long long* i64, cudaStream_t st);
@@ -134,6 +134,39 @@ block_chain_step_kernel(const __grid_constant__ ChainStepBatch B, int C, int Hin
   const float2 g = __ldg(reinterpret_cast<const float2*>(B.grid[z]) + opix);
   const GsTap t = gs_setup<NM>(g.x, g.y, Hin, Win, false);
   gs_fetch_all_cg<NM>(B.src[z], static_cast<long long>(Hin) * Win, t, Win, C, B.dst[z] + opix, Hg * Wg);
+}
+
+// Step 1 of the chains with the key frames at DECODER resolution [C,hl,wl]: the reference samples
+// up(key) = F.interpolate(key, (H,W), bilinear, align_corners=True) (flow/model.py:191-193, 205-206, 214); here each of
+// the four taps of a grid point is that up-sample evaluated at the tap's pixel (up_fetch: the arithmetic of
+// fuvs_upsample_bilinear_ac), so the full-resolution key frame is never materialised.  16 loads per point and channel,
+// 8 040 points per side.
+template <class NM>
+__global__ void __launch_bounds__(256)
+block_chain_step1_lowres_kernel(const __grid_constant__ ChainStepBatch B, int C, int hl, int wl, int H, int W, int Hg,
+                                int Wg, float shk, float swk) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  if (x >= Wg || y >= Hg) return;
+  const int z = blockIdx.z;
+  const int opix = y * Wg + x;
+  const float2 g = __ldg(reinterpret_cast<const float2*>(B.grid[z]) + opix);
+  const GsTap t = gs_setup<NM>(g.x, g.y, H, W, false);
+  const UpCoord hn = up_coord<NM>(shk, t.iy, hl), hs = up_coord<NM>(shk, t.iy + t.dy, hl);
+  const UpCoord ww = up_coord<NM>(swk, t.ix, wl), we = up_coord<NM>(swk, t.ix + t.dx, wl);
+  const int lplane = hl * wl, out_plane = Hg * Wg;
+  const float* src = B.src[z];
+  float* dst = B.dst[z] + opix;
+  for (int c = 0; c < C; ++c) {
+    const float* pl = src + c * lplane;
+    float acc = tap_acc<NM>(0.f, up_fetch<NM>(pl, wl, hn, ww), t.nw);
+    if (t.dx) acc = tap_acc<NM>(acc, up_fetch<NM>(pl, wl, hn, we), t.ne);
+    if (t.dy) acc = tap_acc<NM>(acc, up_fetch<NM>(pl, wl, hs, ww), t.sw);
+    if (t.dx & t.dy) acc = tap_acc<NM>(acc, up_fetch<NM>(pl, wl, hs, we), t.se);
+    dst[c * out_plane] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -440,12 +473,20 @@ namespace fuvs {
 // the temporal counts were fused.
 static int block_frames(const float* prev, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
                         int n, uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
-                        int ignore_index, cudaStream_t st, bool* counts_done) {
+                        int ignore_index, cudaStream_t st, bool* counts_done, int hl, int wl) {
   *counts_done = false;
   if (!labels && !logits) return FUVS_OK;
   BlendWeights w;
   make_blend_weights(n, &w);
   const float sh = ac_scale(Hg, H), sw = ac_scale(Wg, W);
+  if (hl > 0) {      // key frame at decoder resolution: only the row kernel evaluates its up-sample on the fly
+    const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts,
+                                           ignore_index, w, st, hl, wl);
+    if (r < 0) return r;
+    if (r > 0) return set_error(FUVS_EINVAL, "block_lowres: shape not supported (see fuvs_block_lowres_supported)");
+    *counts_done = counts != nullptr;
+    return FUVS_OK;
+  }
   if (Hg == H && Wg == W) {
     // sizes already match: the reference skips the interpolate call (flow/model.py:217), per-pixel kernel
     dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
@@ -459,7 +500,7 @@ static int block_frames(const float* prev, const float* Lst, const float* Rst, i
   }
   // source-row intervals (block_rows.cu) for the shapes it takes (2 <= C <= 5, W % 4 == 0), column strips otherwise
   const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts,
-                                         ignore_index, w, st);
+                                         ignore_index, w, st, 0, 0);
   if (r < 0) return r;
   if (r == 0) {
     *counts_done = counts != nullptr;
@@ -501,7 +542,8 @@ static int block_frames(const float* prev, const float* Lst, const float* Rst, i
 static int block_clip_impl(int m, const float* const* keys, const float* const* gl, const float* const* gr, int C,
                            int H, int W, int Hg, int Wg, int n, float* scratch, uint8_t* const* labels,
                            float* const* logits, const uint8_t* tc_prev, long long* counts, int ignore_index,
-                           cudaStream_t st, const char* who) {
+                           cudaStream_t st, const char* who, int hl = 0, int wl = 0) {
+  // hl > 0: the key frames are given at decoder resolution [C,hl,wl] (n > 1 only; the caller has checked the shape)
   if (int e = device_ok()) return e;
   if (m < 1 || !keys || C < 1 || H < 1 || W < 1 || n < 1)
     return set_error(FUVS_EINVAL, "%s: bad shape m=%d C=%d H=%d W=%d n=%d", who, m, C, H, W, n);
@@ -550,7 +592,7 @@ static int block_clip_impl(int m, const float* const* keys, const float* const* 
   // stream is being captured (kernel-to-kernel latency inside a graph is below a grid-wide barrier: 62.7 vs 65.8 us
   // per 1080p interval) or for several intervals: n-1 launches, each advancing every chain of the batch by one step.
   bool chains_done = false;
-  if (m == 1) {
+  if (m == 1 && hl == 0) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
     if (cap != cudaStreamCaptureStatusActive) {
@@ -595,7 +637,10 @@ static int block_clip_impl(int m, const float* const* keys, const float* const* 
         dim3 cgrid((Wg + 31) / 32, (Hg + 7) / 8, 2 * mb), cblock(32, 8);
         // plain launches on purpose: with programmatic stream serialization the early-launched CTAs of the later steps
         // and of the frame kernel sit on the SMs the running step needs (r01: 97 vs 63 us per 1080p interval)
-        block_chain_step_kernel<Nm><<<cgrid, cblock, 0, st>>>(b, C, Hin, Win, Hg, Wg);
+        if (j == 1 && hl > 0)
+          block_chain_step1_lowres_kernel<Nm><<<cgrid, cblock, 0, st>>>(b, C, hl, wl, H, W, Hg, Wg, ac_scale(hl, H), ac_scale(wl, W));
+        else
+          block_chain_step_kernel<Nm><<<cgrid, cblock, 0, st>>>(b, C, Hin, Win, Hg, Wg);
         if (int e = check_launch("fuvs_block_interval(chain)")) return e;
       }
     }
@@ -608,7 +653,7 @@ static int block_clip_impl(int m, const float* const* keys, const float* const* 
     const uint8_t* tp = (i == 0) ? tc_prev : (want_labels ? labels[i - 1] + (n - 1) * HW : nullptr);
     bool counts_done = false;
     if (int e = block_frames(keys[i], Lst, Rst, C, H, W, Hg, Wg, n, lab, want_logits ? logits[i] : nullptr, tp, counts,
-                             ignore_index, st, &counts_done))
+                             ignore_index, st, &counts_done, hl, wl))
       return e;
     if (counts && !counts_done) {
       if (int e = launch_temporal_counts(lab, n, HW, tp, C, ignore_index, counts, st)) return e;
@@ -646,6 +691,49 @@ extern "C" int fuvs_block_interval(const float* prev, const float* next, const f
   }
   return fuvs_block_interval_ptrs(prev, next, gl, gr, C, H, W, Hg, Wg, n, scratch, labels, logits, tc_prev, counts,
                                   ignore_index, stream);
+}
+
+extern "C" int fuvs_block_lowres_supported(int C, int hl, int wl, int H, int W, int Hg, int Wg) {
+  if (C < 2 || C > 5 || (W & 3) != 0 || hl < 1 || wl < 1 || H < 1 || W < 1 || Hg < 1 || Wg < 1) return 0;
+  if (H == Hg && W == Wg) return 0;
+  // the row kernel stages at most 4 low-resolution key-frame rows per source-row interval of the grid
+  const float sh = fuvs::ac_scale(Hg, H), shk = fuvs::ac_scale(hl, H);
+  int y = 0;
+  while (y < H) {
+    const int i0 = static_cast<int>(sh * static_cast<float>(y));
+    int y_hi = y;
+    while (y_hi < H && static_cast<int>(sh * static_cast<float>(y_hi)) == i0) ++y_hi;
+    const int first = static_cast<int>(shk * static_cast<float>(y)), last = static_cast<int>(shk * static_cast<float>(y_hi - 1));
+    if (last + ((last < hl - 1) ? 1 : 0) - first + 1 > 4) return 0;
+    y = y_hi;
+  }
+  return 1;
+}
+
+extern "C" int fuvs_block_lowres_interval_ptrs(const float* prev_lr, const float* next_lr, int hl, int wl,
+                                               const float* const* grids_left, const float* const* grids_right, int C,
+                                               int H, int W, int Hg, int Wg, int n, float* scratch, uint8_t* labels,
+                                               float* logits, const uint8_t* tc_prev, long long* counts,
+                                               int ignore_index, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (hl == H && wl == W)     // the reference skips the interpolate when the sizes match (flow/model.py:191)
+    return fuvs_block_interval_ptrs(prev_lr, next_lr, grids_left, grids_right, C, H, W, Hg, Wg, n, scratch, labels, logits,
+                                    tc_prev, counts, ignore_index, stream);
+  if (n < 2 || !next_lr) return set_error(FUVS_EINVAL, "block_lowres: needs n >= 2 and both key frames (n=%d)", n);
+  if (!fuvs_block_lowres_supported(C, hl, wl, H, W, Hg, Wg))
+    return set_error(FUVS_EINVAL, "block_lowres: needs 2 <= C <= 5, W %% 4 == 0, a grid coarser than the frame and a key "
+                     "frame no finer than ~4 source rows per grid row (C=%d %dx%d -> %dx%d, grid %dx%d); up-sample with "
+                     "fuvs_upsample_bilinear_ac and call fuvs_block_interval instead", C, hl, wl, H, W, Hg, Wg);
+  if (counts && ignore_index >= 0 && ignore_index < C)
+    return set_error(FUVS_EINVAL, "block_lowres: ignore_index=%d collides with a class", ignore_index);
+  if ((logits && !aligned16(logits)) || (labels && !aligned4(labels)) || (tc_prev && !aligned4(tc_prev)))
+    return set_error(FUVS_EALIGN, "block_lowres: logits must be 16-byte, label maps 4-byte aligned");
+  if (counts && !labels) return set_error(FUVS_EINVAL, "block_lowres: counts need the label maps (labels is NULL)");
+  const float* keys[2] = {prev_lr, next_lr};
+  uint8_t* labs[1] = {labels};
+  float* logs[1] = {logits};
+  return block_clip_impl(1, keys, grids_left, grids_right, C, H, W, Hg, Wg, n, scratch, labs, logs, tc_prev, counts,
+                         ignore_index, static_cast<cudaStream_t>(stream), "block_lowres", hl, wl);
 }
 
 extern "C" int fuvs_block_clip(int m, const float* const* keys, const float* const* grids_left,

@@ -24,15 +24,23 @@ namespace {
 
 constexpr int BR_THREADS = 256;      // two CTAs per SM: one CTA's phase 1 overlaps the other's phase 2
 
-template <int CT, bool COUNTS, bool LOGITS>
+constexpr int KROWS = 4;             // KLR: source rows of the decoder-resolution key frame one CTA may touch
+
+// KLR: key0 is the key frame at DECODER resolution [CT,hl,wl]: frame 0 = arg-max of its
+// up-sample (F.interpolate(bilinear, align_corners=True), flow/model.py:191-193), evaluated like the chain states — the
+// horizontal two-terms of the <= KROWS source rows this CTA's output rows touch are staged once, each output row is one
+// vertical two-term.  The 41 MB full-resolution key frame is neither written by an up-sample launch nor read here.
+template <int CT, bool COUNTS, bool LOGITS, bool KLR>
 __global__ void __launch_bounds__(BR_THREADS, 2)
 block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst, const float* __restrict__ Rst, int H,
                   int W, int Hg, int Wg, int n, float sh, float sw, int XW, int nchunks, int rsplit,
                   uint8_t* __restrict__ labels, float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
-                  unsigned long long* __restrict__ counts, int ignore_index, const BlendWeights wts, float one) {
+                  unsigned long long* __restrict__ counts, int ignore_index, const BlendWeights wts, float one,
+                  int hl, int wl, float shk, float swk) {
   extern __shared__ __align__(16) float br_hs[];            // [p-1][side][row][c][XW], then the key-frame staging slots
   __shared__ unsigned sh24[24];
-  float* key_stage = br_hs + static_cast<size_t>(4) * (n - 1) * CT * XW;     // [BR_THREADS][CT][4]
+  // full-resolution key frame: [BR_THREADS][CT][4] cp.async slots; KLR: [KROWS][CT][XW] horizontal two-terms
+  float* key_stage = br_hs + static_cast<size_t>(4) * (n - 1) * CT * XW;
   using FC = FieldCfg<CT>;
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x / nchunks, chunk = blockIdx.x - i0 * nchunks;
@@ -62,6 +70,8 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
   if (y_hi > y_lo) {
     // ---- phase 1: horizontal two-terms (UpSample.cuh: w0*a + w1*b) of source rows i0, i0 + ip, every state
     const int ip_h = (i0 < Hg - 1) ? 1 : 0;
+    // KLR: first source row of the key frame under this CTA's output rows (same float arithmetic as up_coord)
+    const int kfirst = KLR ? static_cast<int>(__fmul_rn(shk, static_cast<float>(y_lo))) : 0;
     // work item = (state, column): 2(n-1) * xw items over all threads of the CTA
     const int nstates = 2 * (n - 1);
     for (int e = tid; e < nstates * xw; e += BR_THREADS) {
@@ -76,6 +86,18 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
         const float* pl = st + c * lplane;
         dst[(0 * CT + c) * XW] = two_term<Nm::kUpInner>(wc.l0, __ldg(pl + o0), wc.l1, __ldg(pl + o0 + wc.ip));
         dst[(1 * CT + c) * XW] = two_term<Nm::kUpInner>(wc.l0, __ldg(pl + o1), wc.l1, __ldg(pl + o1 + wc.ip));
+      }
+    }
+    if (KLR) {
+      for (int e = tid; e < KROWS * xw; e += BR_THREADS) {
+        const int r = e / xw, xx = e - r * xw;
+        const UpCoord wc = up_coord<Nm>(swk, x0 + xx, wl);
+        const int o = min(kfirst + r, hl - 1) * wl + wc.i0;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const float* pl = key0 + c * (hl * wl);
+          key_stage[(r * CT + c) * XW + xx] = two_term<Nm::kUpInner>(wc.l0, __ldg(pl + o), wc.l1, __ldg(pl + o + wc.ip));
+        }
       }
     }
     __syncthreads();
@@ -96,12 +118,14 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
         // same for the previous interval's last label map (target of frame 0): loaded here, used at the very end
         const bool have_tc = COUNTS && tc_prev != nullptr;
         const unsigned tc_word = have_tc ? PixIO<2>::load_labels(tc_prev + pix) : 0u;
+        if (!KLR) {
 #pragma unroll
-        for (int c = 0; c < CT; ++c) {
-          const unsigned dsts = static_cast<unsigned>(__cvta_generic_to_shared(kslot + c * 4));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(key0 + c * HW + pix) : "memory");
+          for (int c = 0; c < CT; ++c) {
+            const unsigned dsts = static_cast<unsigned>(__cvta_generic_to_shared(kslot + c * 4));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(key0 + c * HW + pix) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
 
         // Labels live as packed float indices {pixel 0, pixel 1}, {pixel 2, pixel 3} (pix4.cuh): the arg-max of a
         // frame without NaN runs in the float domain, a frame with NaN / Inf takes the exact scan and converts.
@@ -200,18 +224,38 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
           }
         }
         // frame 0: the key frame itself (flow/model.py:195-197), then the pairs (0, previous interval) and (1, 0)
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!KLR) asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (COUNTS && 4 * since_spill + 8 > FC::CAP) cnt.spill();       // room for the two pairs below
         {
           u64 xp[2][CT];
+          if (KLR) {
+            const UpCoord kh = up_coord<Nm>(shk, y, hl);
+            const u64 kl0 = pack2(kh.l0, kh.l0), kl1 = pack2(kh.l1, kh.l1);
+            const float* ka = key_stage + static_cast<size_t>((kh.i0 - kfirst) * CT) * XW + xx;
+            const float* kb = ka + static_cast<size_t>(kh.ip * CT) * XW;
 #pragma unroll
-          for (int c = 0; c < CT; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(kslot + c * 4);
-            xp[0][c] = pack2(v.x, v.y);
-            xp[1][c] = pack2(v.z, v.w);
-            if (LOGITS) {
-              const float xs[4] = {v.x, v.y, v.z, v.w};
-              PixIO<2>::store(logits + c * HW + pix, xs);
+            for (int c = 0; c < CT; ++c) {
+              const ulonglong2 f0 = *reinterpret_cast<const ulonglong2*>(ka + c * XW);
+              const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(kb + c * XW);
+              xp[0][c] = two_term2<Nm::kUpOuter>(kl0, f0.x, kl1, f1.x, one2);
+              xp[1][c] = two_term2<Nm::kUpOuter>(kl0, f0.y, kl1, f1.y, one2);
+              if (LOGITS) {
+                float xs[4];
+                unpack2(xp[0][c], xs[0], xs[1]);
+                unpack2(xp[1][c], xs[2], xs[3]);
+                PixIO<2>::store(logits + c * HW + pix, xs);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+              const float4 v = *reinterpret_cast<const float4*>(kslot + c * 4);
+              xp[0][c] = pack2(v.x, v.y);
+              xp[1][c] = pack2(v.z, v.w);
+              if (LOGITS) {
+                const float xs[4] = {v.x, v.y, v.z, v.w};
+                PixIO<2>::store(logits + c * HW + pix, xs);
+              }
             }
           }
           u64 idx0[2];
@@ -245,10 +289,29 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
   if (COUNTS) cnt.finish(sh24, counts, CT);
 }
 
-template <int CT>
+// KLR eligibility: the output rows of every source-row interval must touch at most KROWS rows of the low-resolution key
+// frame (same row arithmetic as the kernel)
+static bool key_rows_fit(int H, int Hg, float sh, int hl, float shk) {
+  auto src_row = [&](int y) { return static_cast<int>(sh * static_cast<float>(y)); };
+  int y = 0;
+  while (y < H) {
+    const int i0 = src_row(y);
+    int y_hi = y;
+    while (y_hi < H && src_row(y_hi) == i0) ++y_hi;
+    const int first = static_cast<int>(shk * static_cast<float>(y));
+    const int last = static_cast<int>(shk * static_cast<float>(y_hi - 1));
+    const int need = last + ((last < hl - 1) ? 1 : 0) - first + 1;
+    if (need > KROWS) return false;
+    y = y_hi;
+  }
+  (void)Hg;
+  return true;
+}
+
+template <int CT, bool KLR>
 int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int W, int Hg, int Wg, int n, float sh,
               float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts, int ignore_index,
-              const BlendWeights& w, cudaStream_t st) {
+              const BlendWeights& w, cudaStream_t st, int hl, int wl, float shk, float swk) {
   // shared memory: (n-1) frames x 2 states x 2 rows x CT channels x XW columns
   const long long per_col = 4ll * (n - 1) * CT * 4;
   const int budget = 108 * 1024 - BR_THREADS * CT * 16;   // two CTAs per SM, minus the key-frame staging slots
@@ -267,7 +330,7 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
   auto cu = reinterpret_cast<unsigned long long*>(counts);
 #define FUVS_BR(CNT_, LG_)                                                                                             \
   do {                                                                                                                 \
-    auto kern = block_rows_kernel<CT, CNT_, LG_>;                                                                      \
+    auto kern = block_rows_kernel<CT, CNT_, LG_, KLR>;                                                                 \
     static SmemOptIn optin;                                                                                            \
     if (!optin.ensure(kern, 110 * 1024)) return 1;                                                                     \
     cudaLaunchConfig_t cfg = {};                                                                                       \
@@ -281,7 +344,7 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
     cfg.attrs = attr;                                                                                                  \
     cfg.numAttrs = 1;                                                                                                  \
     const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, XW, nchunks, rsplit, \
-                                              labels, logits, tc_prev, cu, ignore_index, w, 1.0f);                     \
+                                              labels, logits, tc_prev, cu, ignore_index, w, 1.0f, hl, wl, shk, swk);   \
     if (le != cudaSuccess) return set_error(FUVS_ECUDA, "fuvs_block_interval(stream rows): %s", cudaGetErrorString(le)); \
   } while (0)
   if (counts) { if (logits) FUVS_BR(true, true); else FUVS_BR(true, false); }
@@ -295,20 +358,34 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
 
 // Returns FUVS_OK if it ran (labels, logits and — when counts != NULL — the temporal counts are done), 1 if the
 // shape is not eligible (the caller uses block_stream_cols_kernel), negative on error.
+// hl > 0: key0 is the key frame at decoder resolution [C,hl,wl] (frame 0 = arg-max of its up-sample).
 int launch_block_stream_rows(const float* key0, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
                              int n, float sh, float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev,
-                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st) {
+                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl) {
   if (C < 2 || C > 5 || (W & 3) != 0 || n < 2) return 1;
-  if (!aligned16(key0) || (logits && !aligned16(logits)) || (labels && !aligned4(labels)) || (tc_prev && !aligned4(tc_prev)))
+  const bool klr = hl > 0;
+  if ((!klr && !aligned16(key0)) || (logits && !aligned16(logits)) || (labels && !aligned4(labels)) || (tc_prev && !aligned4(tc_prev)))
     return 1;
   if (counts && ((ignore_index >= 0 && ignore_index < C) || !labels)) return 1;
   if (H == Hg && W == Wg) return 1;                 // nothing to up-sample: per-pixel kernel
-  switch (C) {
-    case 2: return launch_ct<2>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, st);
-    case 3: return launch_ct<3>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, st);
-    case 4: return launch_ct<4>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, st);
-    default: return launch_ct<5>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, st);
+  float shk = 0.f, swk = 0.f;
+  if (klr) {
+    shk = H > 1 ? static_cast<float>(hl - 1) / (H - 1) : 0.f;       // area_pixel_compute_scale, align_corners=True
+    swk = W > 1 ? static_cast<float>(wl - 1) / (W - 1) : 0.f;
+    if (static_cast<long long>(C) * hl * wl >= (1ll << 31) || !key_rows_fit(H, Hg, sh, hl, shk)) return 1;
   }
+#define FUVS_BRC(CT_)                                                                                                  \
+  return klr ? launch_ct<CT_, true>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, \
+                                    st, hl, wl, shk, swk)                                                               \
+             : launch_ct<CT_, false>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, \
+                                     w, st, 0, 0, 0.f, 0.f)
+  switch (C) {
+    case 2: FUVS_BRC(2);
+    case 3: FUVS_BRC(3);
+    case 4: FUVS_BRC(4);
+    default: FUVS_BRC(5);
+  }
+#undef FUVS_BRC
 }
 
 }  // namespace fuvs

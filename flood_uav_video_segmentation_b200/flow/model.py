@@ -212,6 +212,11 @@ class FlowModel(nn.Module):
         self.reset_keyframe_cache()
         return super().load_state_dict(*args, **kwargs)
 
+    def _keeps_lowres(self, mvs_left, h, w):
+        """Routes whose kernels evaluate the key frames' up-sample themselves: linear and
+        block-grid.  The dense route samples the full-resolution key frames through its TMA window."""
+        return self._interval_mode(mvs_left, h, w) in ("linear", "block")
+
     def _interval_mode(self, mvs_left, h, w):
         if self.no_warp or len(mvs_left) == 0 or not _is_grid(mvs_left[0]):
             return "linear"
@@ -237,11 +242,15 @@ class FlowModel(nn.Module):
             if (o.shape[2], o.shape[3]) != (h, w):            # key frames still at decoder resolution
                 return kernels.linear_lowres_blend_argmax(o, o_next, (h, w), n, **kw)
             return kernels.linear_blend_argmax(o, o_next, n, **kw)
-        if (o.shape[2], o.shape[3]) != (h, w):                # warp modes consume full-resolution key frames
-            o = _interp_ac(o, h, w)
-            o_next = _interp_ac(o_next, h, w) if o_next is not None else None
         if len(mvs_left) != n - 1 or len(mvs_right) != n - 1:
             raise FuvsError(f"FlowModel.predict: n={n} needs {n - 1} grids per side, got {len(mvs_left)}/{len(mvs_right)}")
+        if mode == "block" and (o.shape[2], o.shape[3]) != (h, w):
+            # key frames still at decoder resolution: the block route evaluates their up-sample inside its kernels
+            # (shapes it does not take are up-sampled by the wrapper: same arithmetic)
+            return kernels.block_lowres_interval(o, o_next, (h, w), mvs_left, mvs_right, n, scratch=self._scratch, **kw)
+        if (o.shape[2], o.shape[3]) != (h, w):                # the dense route consumes full-resolution key frames
+            o = _interp_ac(o, h, w)
+            o_next = _interp_ac(o_next, h, w) if o_next is not None else None
         if mode == "dense":
             return kernels.dense_interval(o, o_next, mvs_left, mvs_right, n, scratch=self._scratch, **kw)
         return kernels.block_interval(o, o_next, mvs_left, mvs_right, n, scratch=self._scratch, **kw)
@@ -249,7 +258,7 @@ class FlowModel(nn.Module):
     def predict_segmentation(self, frame_prev, frame_next, mvs_left, mvs_right, n, profiler):
         """flow/model.py:184-241 -> {"pred": [n,C,h,w]} (frame 0 = key-frame logits)."""
         h, w = frame_prev.shape[2], frame_prev.shape[3]
-        lowres = bool(self.no_warp) and frame_next is not None
+        lowres = self._keeps_lowres(mvs_left, h, w) and frame_next is not None
         o = self._keyframe_logits(frame_prev, h, w, profiler, keep_lowres=lowres)
         if frame_next is None:
             return {"pred": o}
@@ -274,7 +283,7 @@ class FlowModel(nn.Module):
             return labels
         h, w = frame_prev.shape[2], frame_prev.shape[3]
         with torch.no_grad():
-            lowres = bool(self.no_warp) and frame_next is not None
+            lowres = self._keeps_lowres(mvs_left, h, w) and frame_next is not None
             o = self._cached_keyframe(frame_id, (h, w), frame_prev.device, lowres)
             if o is None:
                 o = self._keyframe_logits(frame_prev, h, w, profiler, keep_lowres=lowres)

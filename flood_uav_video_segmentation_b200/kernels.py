@@ -200,6 +200,39 @@ def block_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, w
     return labels, logits
 
 
+def block_lowres_interval(prev_lr, nxt_lr, size, grids_left, grids_right, n, *, want_labels=True, want_logits=False,
+                          tc_prev=None, counts=None, ignore_index=255, scratch=None):
+    """fuvs_block_lowres_interval_ptrs: key frames at decoder resolution [C,hl,wl] / [1,C,hl,wl], frame size `size`.
+    Shapes the fused kernels do not take go through fuvs_upsample_bilinear_ac + fuvs_block_interval — the same arithmetic
+    in three launches."""
+    dev = require_cuda(prev_lr, nxt_lr, tc_prev, counts, what="block_lowres_interval")
+    prev_lr = _f32c(prev_lr, "prev_lr")
+    C, hl, wl = prev_lr.shape[-3:]
+    H, W = int(size[0]), int(size[1])
+    gl = _grid_list(grids_left, n, None, dev, "block_lowres_interval(grids_left)") if n > 1 else []
+    Hg, Wg = (gl[0].shape[:2] if n > 1 else (0, 0))
+    ok = n > 1 and load().fuvs_block_lowres_supported(C, hl, wl, H, W, Hg, Wg) and not (counts is not None and 0 <= ignore_index < C)
+    if not ok or (hl, wl) == (H, W):
+        up = upsample_bilinear_ac(prev_lr.reshape(1, C, hl, wl), (H, W))
+        up_n = upsample_bilinear_ac(_f32c(nxt_lr, "next_lr").reshape(1, C, hl, wl), (H, W)) if n > 1 else None
+        return block_interval(up, up_n, grids_left, grids_right, n, want_labels=want_labels, want_logits=want_logits,
+                              tc_prev=tc_prev, counts=counts, ignore_index=ignore_index, scratch=scratch)
+    nxt_lr = _f32c(nxt_lr, "next_lr")
+    if nxt_lr.shape[-3:] != prev_lr.shape[-3:]:
+        raise FuvsError("block_lowres_interval: key frames differ in shape")
+    gl = _grid_list(gl, n, (Hg, Wg), dev, "block_lowres_interval(grids_left)")
+    gr = _grid_list(grids_right, n, (Hg, Wg), dev, "block_lowres_interval(grids_right)")
+    scratch = _scratch(scratch, int(load().fuvs_block_scratch_floats(C, Hg, Wg, n)), dev)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    with torch.cuda.device(dev):
+        check(load().fuvs_block_lowres_interval_ptrs(ptr(prev_lr), ptr(nxt_lr), hl, wl, ptr_array(gl), ptr_array(gr), C, H, W,
+                                                     Hg, Wg, n, ptr(scratch), ptr(labels), ptr(logits), ptr(tc_prev),
+                                                     ptr(counts), ignore_index, stream_ptr(dev)))
+    return labels, logits
+
+
 def block_clip(keys, grids_left, grids_right, n, *, want_logits=False, tc_prev=None, counts=None, ignore_index=255,
                scratch=None):
     """fuvs_block_clip: m consecutive intervals of one clip in one call.  keys: m+1 key-frame logit maps [1,C,H,W] /

@@ -195,6 +195,20 @@ FUVS_API int fuvs_block_interval_ptrs(const float* prev, const float* next,
                         uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts,
                         int ignore_index, fuvs_stream_t stream);
+/* The key frames at DECODER resolution [C,hl,wl]: prev = up(prev_lr), next = up(next_lr) with
+ * up = F.interpolate(bilinear, align_corners=True) to (H,W) (flow/model.py:191-193, 205-206), evaluated inside the kernels
+ * — the first chain step samples the up-sample at its 4 taps, frame 0 is the arg-max of the up-sample — so the two
+ * full-resolution key frames (2*C*H*W*4 bytes) are never written or read.  Bit-identical to fuvs_upsample_bilinear_ac +
+ * fuvs_block_interval.  Supported when fuvs_block_lowres_supported(...) != 0 (2 <= C <= 5, W % 4 == 0, at most four
+ * key-frame rows under one grid row); hl==H && wl==W forwards to fuvs_block_interval_ptrs. */
+FUVS_API int fuvs_block_lowres_supported(int C, int hl, int wl, int H, int W, int Hg, int Wg);
+FUVS_API int fuvs_block_lowres_interval_ptrs(const float* prev_lr, const float* next_lr, int hl, int wl,
+                        const float* const* grids_left_host, const float* const* grids_right_host,
+                        int C, int H, int W, int Hg, int Wg, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
 /* m CONSECUTIVE intervals of one clip in one call (what m successive predict_step calls compute, flow/base.py:259-295):
  * interval i lies between keys_host[i] and keys_host[i+1] (m+1 key-frame logit maps), uses the grids
  * grids_*_host[i*(n-1) .. i*(n-1)+n-2], writes labels_host[i] ([n,H,W]) and logits_host[i] (or NULL arrays), and its

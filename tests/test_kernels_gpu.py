@@ -575,3 +575,33 @@ def test_grid_lists_are_passed_by_pointer(cuda):
         a = fn(o, o_next, torch.cat(gl, 0), torch.cat(gr, 0), n, want_logits=True)
         b = fn(o, o_next, views, gr, n, want_logits=True)
         assert torch.equal(a[0], b[0]) and bits_equal(a[1], b[1]), mode
+
+
+@pytest.mark.parametrize("C,hl,wl,H,W", [(5, 135, 240, 1080, 1920), (5, 134, 240, 1072, 1920), (2, 34, 60, 272, 480),
+                                         (5, 17, 25, 136, 200), (3, 30, 40, 64, 96), (5, 55, 55, 433, 433),
+                                         (7, 12, 16, 96, 128), (5, 64, 96, 64, 96)])
+@pytest.mark.parametrize("n", [2, 5])
+def test_block_lowres_interval(cuda, C, hl, wl, H, W, n):
+    """Block-grid route with the key frames at decoder resolution: first chain step and frame 0
+    evaluate F.interpolate(bilinear, align_corners=True) on the fly.  Labels, logits and counts bit-exact against
+    F.interpolate + the reference sequence on torch-CUDA.  433x433 / C=7 / a too fine key frame take the wrapper's
+    three-launch route, (5,64,96,64,96) forwards to the plain entry."""
+    g = torch.Generator().manual_seed(C * 1000 + hl + n)
+    o_lr = (torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda)
+    o_next_lr = (torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda)
+    up = (lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)) if (hl, wl) != (H, W) else (lambda t: t)
+    gl = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=7, side=0)]
+    gr = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=7, side=1)]
+    ref_logits = fo.predict_segmentation(ident, ident, up(o_lr), up(o_next_lr), gl, gr, n, no_warp=False)
+    ref_labels = fo.argmax_labels(ref_logits)
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)
+    counts = kernels.new_counts(C, cuda)
+    labels, logits = kernels.block_lowres_interval(o_lr, o_next_lr, (H, W), gl, gr, n, want_labels=True, want_logits=True,
+                                                   tc_prev=tc_prev.to(cuda), counts=counts)
+    bad = int((logits.view(torch.int32) != ref_logits.view(torch.int32)).sum())
+    assert bad == 0, f"{bad} logits differ from F.interpolate + the reference sequence"
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy(), ref_counts)
+    labels2, none = kernels.block_lowres_interval(o_lr, o_next_lr, (H, W), gl, gr, n)
+    assert none is None and torch.equal(labels2, labels)
