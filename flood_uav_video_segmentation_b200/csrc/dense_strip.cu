@@ -336,7 +336,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 #pragma unroll
       for (int r = 0; r < PX; ++r) {
         const int y = yb + ty + r * TROWS;
-        dstg[r] = (on && vx && (FULLV || y < H)) ? __ldg(grid + y * W + x) : make_float2(0.f, 0.f);
+        dstg[r] = (on && vx && (FULLV || y < H)) ? __ldcs(grid + y * W + x) : make_float2(0.f, 0.f);   // read once: evict first
       }
     };
     auto load_other = [&](int yb, bool on, float (&dsto)[PX][CR]) {
@@ -346,12 +346,12 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         const int y = yb + ty + r * TROWS;
         const bool live = on && vx && (FULLV || y < H);
         if constexpr (IL) {
-          const float4 q = live ? __ldg(reinterpret_cast<const float4*>(point) + (y * W + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 q = live ? __ldcs(reinterpret_cast<const float4*>(point) + (y * W + x)) : make_float4(0.f, 0.f, 0.f, 0.f);
           dsto[r][0] = q.x; dsto[r][1] = q.y; dsto[r][2] = q.z; dsto[r][3] = q.w;
-          dsto[r][CR - 1] = live ? __ldg(point + (4 * HWi + y * W + x)) : 0.f;
+          dsto[r][CR - 1] = live ? __ldcs(point + (4 * HWi + y * W + x)) : 0.f;
         } else {
 #pragma unroll
-          for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldg(point + (c * HWi + y * W + x)) : 0.f;
+          for (int c = 0; c < CR; ++c) dsto[r][c] = live ? __ldcs(point + (c * HWi + y * W + x)) : 0.f;   // last use of that state
         }
       }
     };
