@@ -791,7 +791,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="dense", choices=["dense", "block", "block_clip", "block_lowres", "linear", "dense_smooth", "linear_lowres"])
-    ap.add_argument("--clips-per-step", type=int, default=36, help="36 clips = 108 intervals: a dense step is ~25 ms")
+    ap.add_argument("--clips-per-step", type=int, default=40, help="40 clips = 120 intervals: a dense step is ~27 ms")
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent clips of a step alternate over")
     ap.add_argument("--no-e2e", action="store_true")

@@ -21,12 +21,13 @@ int set_error(int code, const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// After a <<<>>> launch.  The error is reported but NOT cleared: if it was already pending when the entry was called (a
+// failed call of another library on this thread, e.g. PyTorch) its owner must still see it; a launch failure of our own
+// is equally visible to the caller's next CUDA check.  (Launches through cudaLaunchKernelEx check its return value.)
 int check_launch(const char* what) {
   const cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return set_error(FUVS_ECUDA, "%s: %s", what, cudaGetErrorString(e));
-  }
+  if (e != cudaSuccess)
+    return set_error(FUVS_ECUDA, "%s: %s (pending CUDA error, not cleared by libfuvs)", what, cudaGetErrorString(e));
   count_launch();
   return FUVS_OK;
 }

@@ -163,15 +163,18 @@ extern "C" int fuvs_crop_grid(const float* grid, int Hg, int Wg, int H, int W, i
   g.bw_off = static_cast<int>(std::nearbyint(w_off / ppb_w));
   g.bh = static_cast<int>(std::nearbyint((h_off + crop_h) / ppb_h)) - g.bh_off;
   g.bw = static_cast<int>(std::nearbyint((w_off + crop_w) / ppb_w)) - g.bw_off;
-  // numpy slicing clips at the array end; an empty slice makes cv2.resize raise in the reference
+  // the re-normalisation divides by the UNCLIPPED block counts (flow/transform.py:238-239) ...
+  const int bh_full = g.bh, bw_full = g.bw;
+  // ... while numpy slicing clips at the array end (:237) and cv2.resize scales from the clipped shape; an empty slice
+  // makes cv2.resize raise in the reference
   if (g.bh_off + g.bh > Hg) g.bh = Hg - g.bh_off;
   if (g.bw_off + g.bw > Wg) g.bw = Wg - g.bw_off;
   if (g.bh < 1 || g.bw < 1)
     return set_error(FUVS_EINVAL, "crop_grid: the crop covers no grid block (cv2.resize would raise in the reference)");
   g.width = static_cast<float>(W); g.height = static_cast<float>(H);
   g.w_off = static_cast<float>(w_off); g.h_off = static_cast<float>(h_off);
-  g.den_x = static_cast<float>(g.bw * ppb_w);
-  g.den_y = static_cast<float>(g.bh * ppb_h);
+  g.den_x = static_cast<float>(bw_full * ppb_w);
+  g.den_y = static_cast<float>(bh_full * ppb_h);
   g.scale_x = static_cast<double>(g.bw) / g.ow;   // cv2: scale = 1 / (dsize / ssize) in double
   g.scale_y = static_cast<double>(g.bh) / g.oh;
   {

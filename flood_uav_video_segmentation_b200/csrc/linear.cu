@@ -684,7 +684,8 @@ static int launch_lowres(const float* prev_lr, const float* next_lr, int hl, int
 #define FUVS_LR(CNT_, LG_)                                                                                              \
   do {                                                                                                                  \
     auto kern = linear_lowres_kernel<CT, CNT_, LG_>;                                                                    \
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) \
+    static SmemOptIn optin;                 /* once per device, for the whole two-CTAs-per-SM budget */                 \
+    if (!optin.ensure(kern, 108 * 1024))                                                                                \
       return set_error(FUVS_ECUDA, "linear_lowres: cannot reserve %zu bytes of shared memory", smem);                   \
     kern<<<grid, LR_THREADS, smem, st>>>(prev_lr, next_lr, hl, wl, H, W, n, sh, sw, XW, nchunks, labels, logits,        \
                                          tc_prev, cu, ignore_index, w, 1.0f);                                           \
