@@ -9,7 +9,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from flood_uav_video_segmentation_b200 import kernels
+from flood_uav_video_segmentation_b200 import _lib, kernels
+
+if os.environ.get("FUVS_DEV_LIB"):          # developer A/B build (build.py FUVS_BUILD_TAG), this tool only
+    _lib.use_library(os.environ["FUVS_DEV_LIB"])
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "dense"
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 2
