@@ -286,3 +286,49 @@ def test_keyframe_cache_is_invalidated_by_weight_and_mode_changes(cuda):
     fm.reuse_keyframes = False
     c = fm.predict_labels(x1, x0, dummy, dummy, n, prof)
     assert torch.equal(b, c) and not torch.equal(a, b)
+
+
+@pytest.mark.parametrize("feature_based,no_warp,no_cropping", [(False, False, True), (False, True, True), (True, False, True),
+                                                               (False, False, False)])
+def test_predict_step_resizes_to_the_output_size(cuda, feature_based, no_warp, no_cropping):
+    """Frames that are NOT at the hard-coded (1072, 1920) of flow/base.py:275: predict_step's
+    F.interpolate(output, size, bilinear, align_corners=True) + max(1)[1] + uint8 (one kernel, fuvs_upsample_argmax; for
+    the sliding-crop route the fp64 canvas goes through torch's interpolate as in the reference) and the temporal metric
+    on the RESIZED label maps, against the restated reference sequence on torch-CUDA."""
+    import torch.nn.functional as F
+    H, W, n, C = 80, 112, 3, 5
+    out_size = (96, 160)
+    bb = TinyBackbone(classes=C).to(cuda).eval()
+    m = FlowBaseModel(classes=C, arch="pspnet", feature_based=feature_based, no_warp=no_warp, no_cropping=no_cropping,
+                      backbone=bb, output_size=out_size, test_h=49, test_w=65, save_video=False).to(cuda).eval()
+    m.on_predict_start()
+    g = torch.Generator().manual_seed(12)
+    keys = [torch.randn(1, 3, H, W, generator=g).to(cuda) for _ in range(3)]
+    tot = [np.zeros(C, np.int64) for _ in range(3)]
+    last = None
+    for it in range(2):
+        if no_warp:
+            gl = gr = [torch.zeros(1, 1, device=cuda)] * (n - 1)
+        else:
+            gl = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=13, interval=it, side=0)]
+            gr = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=13, interval=it, side=1)]
+        out = m.predict_step({"frame_prev": keys[it], "frame_next": keys[it + 1], "mvs_left": gl, "mvs_right": gr}, it)
+        assert tuple(out.shape) == (n,) + out_size and out.dtype == torch.uint8
+        if not no_cropping:
+            continue              # reference canvas: covered bit-exactly at canvas size by tests/test_crop_gpu.py
+        with torch.no_grad():
+            if feature_based:
+                logits = fo.predict_feature(bb.encoder, bb.decoder, keys[it], keys[it + 1], gl, gr, n,
+                                            m.model_G.default_motion_vector, no_warp=no_warp)
+            else:
+                logits = fo.predict_segmentation(bb.encoder, bb.decoder, keys[it], keys[it + 1], gl, gr, n, no_warp=no_warp)
+            ref = F.interpolate(logits, out_size, mode="bilinear", align_corners=True).max(1)[1]      # flow/base.py:275-276
+        assert torch.equal(out.long(), ref)
+        (i, u, t), last = mo.temporal_consistency_counts(ref.cpu().numpy(), C, 255, last)
+        for acc, v in zip(tot, (i, u, t)):
+            acc += v
+    m.on_predict_end()
+    if no_cropping:
+        assert np.array_equal(m.intersection_meter_predict.sum, tot[0])
+        assert np.array_equal(m.union_meter_predict.sum, tot[1])
+        assert np.array_equal(m.target_meter_predict.sum, tot[2])
