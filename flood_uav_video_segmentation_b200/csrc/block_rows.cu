@@ -74,6 +74,9 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
     const int kfirst = KLR ? static_cast<int>(__fmul_rn(shk, static_cast<float>(y_lo))) : 0;
     // work item = (state, column): 2(n-1) * xw items over all threads of the CTA
     const int nstates = 2 * (n - 1);
+    // (four items in flight: the 4*CT gathers of an item are L2 round trips, and eight dependent rounds per thread were
+    // 11 % of the warp time, profiles/r02_ncu_block_rows.txt; measured 57.2 -> 53.8 us per interval, unroll 8: 54.8)
+#pragma unroll 4
     for (int e = tid; e < nstates * xw; e += BR_THREADS) {
       const int sidx = e / xw, xx = e - sidx * xw;          // sidx = (p-1)*2 + side
       const int p = (sidx >> 1) + 1, side = sidx & 1;
