@@ -230,6 +230,14 @@ block_stream_kernel(const float* __restrict__ key0, const float* __restrict__ Ls
   }
 }
 
+// ld.global.cg with a 64-byte L2 fetch granularity: the taps of a grid point are scattered 4-byte reads (step 1: from
+// the cold full-resolution key frames), a 128-byte fill per tap row would move 52 MB for 1.3 MB of useful data
+__device__ __forceinline__ float ld_cg_64(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // All C channels of one grid point: the tap loads of up to 8 channels are issued before the first store.  Written as
 // `dst[c] = gs_fetch_cg(src + c)` the store of channel c — which may alias the source for all the compiler knows (both
 // live in the chain scratch) — keeps the loads of channel c+1 behind it in program order: C dependent L2 round
@@ -246,7 +254,7 @@ __device__ __forceinline__ void gs_fetch_all_cg(const float* src, long long in_p
     for (int u = 0; u < U; ++u) {
       if (c0 + u < C) {
         const float* q = p + (c0 + u) * in_plane;
-        v00[u] = __ldcg(q); v01[u] = __ldcg(q + o01); v10[u] = __ldcg(q + o10); v11[u] = __ldcg(q + o11);
+        v00[u] = ld_cg_64(q); v01[u] = ld_cg_64(q + o01); v10[u] = ld_cg_64(q + o10); v11[u] = ld_cg_64(q + o11);
       }
     }
 #pragma unroll
