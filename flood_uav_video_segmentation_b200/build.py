@@ -30,8 +30,6 @@ _TAG = os.environ.get("FUVS_BUILD_TAG", "")
 if _TAG:
     LIB = os.path.join(LIBDIR, f"libfuvs_{_TAG}.so")
     NVCC_FLAGS += os.environ.get("FUVS_BUILD_DEFINES", "").split()
-if os.environ.get("FUVS_STRIP_PROF"):   # developer instrumentation of dense_strip.cu (never set for the shipped build)
-    NVCC_FLAGS.append("-DFUVS_STRIP_PROF")
 
 
 def _nvcc() -> str:

@@ -37,7 +37,13 @@
 //              planar key frames and writes 4+1; measured 239 -> 22x us per interval.
 //   taps     : a warp whose taps leave the window (large motion) gathers its pixels of that block from global memory
 //              instead, so any flow field stays correct.
-//   counts   : stay in fuvs_temporal_counts (metric.cu).
+//   counts   : stay in fuvs_temporal_counts (metric.cu), 8 us of stream time behind the last step (nothing can share an
+//              SM with a strip CTA, which holds all registers).  Measured in r02 and rejected: counting inside the block
+//              loop (two more loads per pixel on the gather's path, 242 vs 230 us); the last step's CTAs counting
+//              their own pixels after a block-wide barrier, labels staged through the dead ring with cp.async
+//              (227.2 / 222.6 us on 1 / 2 streams against 228.0 / 221.0 for the separate launch, both with the
+//              bit-plane counters of temporal_fields.cuh); every warp counting its own pixels as soon as it is done,
+//              without a barrier (236.7 / 230.1: the unrolled counting code is fetched cold by one warp after the other).
 // Arithmetic is gs_setup/tap_acc/blend2 from fuvs_common.cuh: bit-identical to the direct kernel (warp.cu) and to
 // ATen's grid_sampler_2d (flow/model.py:244-249).
 #include <type_traits>

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "fuvs_common.cuh"
+#include "temporal_fields.cuh"
 
 namespace fuvs {
 
@@ -118,36 +119,6 @@ static int persistent_grid(K kernel, long long work_items, int threads) {
 // per iteration with 128-bit loads, counts in three 32-bit registers with 6/8-bit class fields (FieldCounts) and the
 // warp reduction happens once per kernel.
 // ---------------------------------------------------------------------------
-template <int KT>
-__device__ __forceinline__ unsigned tc_invalid(const uint4& w) {
-  constexpr unsigned ADD = (0x80u - KT) * 0x01010101u;
-  const unsigned a = (((w.x & 0x7f7f7f7fu) + ADD) | w.x), b = (((w.y & 0x7f7f7f7fu) + ADD) | w.y);
-  const unsigned c = (((w.z & 0x7f7f7f7fu) + ADD) | w.z), d = (((w.w & 0x7f7f7f7fu) + ADD) | w.w);
-  return (a | b | c | d) & 0x80808080u;
-}
-__device__ __forceinline__ unsigned tc_one_shl_wrap(unsigned c) {
-  unsigned d;
-  asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(1u), "r"(c));
-  return d;
-}
-template <int KT>
-__device__ __forceinline__ unsigned tc_fields(const uint4& w, unsigned (&fld)[16]) {
-  constexpr unsigned FW = FieldCfg<KT>::FW;
-  const unsigned ws[4] = {w.x, w.y, w.z, w.w};
-  unsigned s = 0u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const unsigned m = ws[j] * FW;             // bytes: FW * label <= 24, the low five bits of each are the shift
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      fld[4 * j + i] = tc_one_shl_wrap(m >> (8 * i));
-      s += fld[4 * j + i];
-    }
-  }
-  return s;
-}
-
-
 // ---------------------------------------------------------------------------
 // Byte-domain counting of one group of 16 (prediction, target) labels for fuvs_confusion's fast path.  The per-label
 // code below it works on 64-bit values (range checks, ignore test and three field updates: ~20 ALU instructions per
@@ -470,83 +441,34 @@ temporal_counts_kernel(const uint8_t* __restrict__ labels, int n, long long HW, 
 }
 
 // Fast path of the temporal-consistency counts: K <= 5, ignore outside [0,K), HW % 16 == 0.  16 pixels per thread
-// (one 128-bit load per frame), field-packed counters (FieldCounts), one REDUX pass per warp at the end.
-// Per label the first version spent ~14 ALU instructions (two byte extractions, range checks and a select for each of
-// output and target, three adds, a compare and a select): 15 us for 5 x 1080p, ALU-bound at 0.8 TB/s.  Now a frame whose
-// 16 labels are all < KT (always, for arg-max output) gets its counter fields from one multiply per word (label bytes
-// times the field width are the shift amounts) and one or two shifts per label; the T term of a pair is the field sum
-// of the previous frame (one add per 16 labels), and the I term is a predicated add on the bytes of cur ^ last.
+// (one 128-bit load per frame), bit-plane counting (temporal_fields.cuh: ~3 ALU instructions per label and frame; the
+// first version spent ~14, the field-packed second one ~9 and 10 us for 5 x 1080p), one REDUX pass per warp at the end.
 // Frames with out-of-range labels (a caller's own label maps, ignore_index) take the per-label path.
 template <int KT>
 __global__ void __launch_bounds__(256)
 temporal_counts_v16_kernel(const uint8_t* __restrict__ labels, int n, long long HW, const uint8_t* __restrict__ tc_prev,
                            int ignore, unsigned long long* __restrict__ counts) {
-  using FC = FieldCfg<KT>;
   __shared__ unsigned sh[24];
   // programmatic dependent launch (see dense_strip.cu): start while the producer of the label maps drains, let the
   // next kernel of the stream do the same, touch memory only after the producer has completed
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  FieldCounts<KT> cnt;
+  ClassCounts<KT> cnt;
   cnt.init();
   const long long nvec = HW >> 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const long long pix = v << 4;
-    uint4 last = make_uint4(0u, 0u, 0u, 0u);
-    bool have_last = false;
-    unsigned bad_last = 0u, s_last = 0u;
-    if (tc_prev) {
-      last = __ldg(reinterpret_cast<const uint4*>(tc_prev + pix));
-      have_last = true;
-      bad_last = tc_invalid<KT>(last);
-      unsigned f[16];
-      s_last = tc_fields<KT>(last, f);          // only used when bad_last == 0
+    if (n == 5) {
+      // the reference's interval (k = 5): all six label words are requested before the first is counted
+      uint4 q[6];
+      q[0] = tc_prev ? __ldg(reinterpret_cast<const uint4*>(tc_prev + pix)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int p = 0; p < 5; ++p) q[p + 1] = __ldcs(reinterpret_cast<const uint4*>(labels + p * HW + pix));
+      tc_chain16_ld<KT, true, 5>(cnt, tc_prev != nullptr, 5, ignore, [&](int p) { return q[p + 1]; });
+    } else {
+      tc_chain16<KT>(cnt, tc_prev ? tc_prev + pix : nullptr, labels + pix, n, HW, ignore);
     }
-    int since_spill = 0;
-    uint4 nxt = __ldcs(reinterpret_cast<const uint4*>(labels + pix));
-    for (int p = 0; p < n; ++p) {
-      const uint4 cur = nxt;
-      if (p + 1 < n)   // software pipelining: the next frame's load is in flight while this one is counted
-        nxt = __ldcs(reinterpret_cast<const uint4*>(labels + static_cast<long long>(p + 1) * HW + pix));
-      const unsigned bad_cur = tc_invalid<KT>(cur);
-      unsigned fld[16];
-      const unsigned s_cur = tc_fields<KT>(cur, fld);
-      if (have_last) {
-        const unsigned cw[4] = {cur.x, cur.y, cur.z, cur.w};
-        const unsigned lw[4] = {last.x, last.y, last.z, last.w};
-        if ((bad_cur | bad_last) == 0u) {
-          cnt.accO += s_cur;
-          cnt.accT += s_last;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const unsigned x = cw[w] ^ lw[w];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) cnt.accI += ((x & (0xffu << (8 * i))) == 0u) ? fld[4 * w + i] : 0u;
-          }
-        } else {
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int o = (cw[w] >> (8 * i)) & 255u, t = (lw[w] >> (8 * i)) & 255u;
-              const unsigned ft = (t < KT) ? FieldCounts<KT>::field(t) : 0u;
-              const unsigned fo = (o < KT && t != ignore) ? FieldCounts<KT>::field(o) : 0u;
-              cnt.add(o, fo, t, ft);
-            }
-          }
-        }
-        if (++since_spill >= FC::CAP / 16) {
-          cnt.spill();
-          since_spill = 0;
-        }
-      }
-      last = cur;
-      bad_last = bad_cur;
-      s_last = s_cur;
-      have_last = true;
-    }
-    cnt.spill();
   }
   cnt.finish(sh, counts, KT);
 }

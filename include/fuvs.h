@@ -306,6 +306,12 @@ FUVS_API int fuvs_confusion(void* pred, int pred_is_i64,
  * Temporal-consistency metric over finished label maps — flow/base.py:280-295:
  * for p in 0..n-1: metric(output=labels[p], target=labels[p-1]) with p=0
  * compared against tc_prev when it is not NULL (skipped otherwise).
+ * A label counts iff it is < K (and, for the output, the target is not
+ * ignore_index).  The reference's numpy metric (util/util.py:36-47) would
+ * also count the value K itself as class K-1 (np.histogram closes its last
+ * bin); arg-max label maps — all the reference ever passes here — never hold
+ * it.  fuvs_confusion's FUVS_BINS_NPHIST reproduces that bin for label maps
+ * that can.
  * ------------------------------------------------------------------------- */
 FUVS_API int fuvs_temporal_counts(const uint8_t* labels, int n, long long HW,
                          const uint8_t* tc_prev, int K, int ignore_index,

@@ -181,6 +181,32 @@ def test_feature_interval(cuda, C, fh, fw, hg, wg, n):
     assert bits_equal(got2[0], f[0]) and bits_equal(got2[1:], ref[1:])
 
 
+@pytest.mark.parametrize("prev_kind", ["none", "labels", "out_of_range"])
+@pytest.mark.parametrize("C,H,W", [(5, 64, 256), (2, 96, 128), (5, 136, 384)])
+@pytest.mark.parametrize("n", [3, 5, 6, 9])
+def test_dense_interval_counts_with_foreign_labels(cuda, C, H, W, n, prev_kind):
+    """The interval's temporal counts (bit-plane counters, temporal_fields.cuh) with and without tc_prev; out-of-range
+    labels in tc_prev (a caller's own map: ignore_index, or neither a class nor ignore_index) take the per-label path;
+    the entry accumulates into the caller's counts."""
+    o, o_next = keyframe_logits(C, H, W, 5, 0)[None], keyframe_logits(C, H, W, 5, 1)[None]
+    gl = flow_grids(H, W, n, "dense", clip=5, side=0)
+    gr = flow_grids(H, W, n, "dense", clip=5, side=1)
+    _, ref_labels = oracle_interval(o, o_next, gl, gr, n, False, cuda)
+    tc_prev = None
+    if prev_kind != "none":
+        tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(n), dtype=torch.uint8)
+        if prev_kind == "out_of_range":
+            tc_prev[::3, ::5] = 255          # ignore_index
+            tc_prev[1::7, 2::11] = C + 1     # neither a class nor ignore_index
+    counts = kernels.new_counts(C, cuda)
+    counts += 7
+    labels, _ = kernels.dense_interval(o.to(cuda), o_next.to(cuda), [g.to(cuda) for g in gl], [g.to(cuda) for g in gr], n,
+                                       tc_prev=None if tc_prev is None else tc_prev.to(cuda), counts=counts)
+    assert torch.equal(labels.long(), ref_labels)
+    ref_counts, _ = oracle_temporal(ref_labels, C, None if tc_prev is None else tc_prev.numpy().astype(np.int64))
+    assert np.array_equal(counts.cpu().numpy() - 7, ref_counts)
+
+
 def test_full_size_1080p_all_modes(cuda):
     """BASELINE.json configs at full size, one interval each, against the oracle on torch-CUDA."""
     C, H, W, n = 5, 1080, 1920, 5
@@ -378,6 +404,29 @@ def test_temporal_counts(cuda, K, H, W):
     g = torch.Generator().manual_seed(K + H)
     labels = torch.randint(0, K, (6, H, W), generator=g, dtype=torch.uint8)
     last = torch.randint(0, K, (H, W), generator=g, dtype=torch.uint8)
+    for prev in (None, last):
+        ref, _ = oracle_temporal(labels.long(), K, None if prev is None else prev.numpy().astype(np.int64))
+        got = kernels.temporal_counts(labels.to(cuda), K, 255, tc_prev=None if prev is None else prev.to(cuda))
+        assert np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("foreign", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 5, 7])
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5])
+def test_temporal_counts_bit_planes(cuda, K, n, foreign):
+    """The 16-labels-per-thread path (K <= 5, HW % 16 == 0): bit-plane counters, n = 5 with all loads up front.  With
+    `foreign`, label maps carry values that are no class: K+1 .. 7 (fit the planes), 8 .. 16 and 200 (do not), 255 =
+    ignore_index — every 16-pixel group that holds one takes the per-label path.  (The value K itself is left out:
+    np.histogram's closed last bin would count it as class K-1, the library counts a value iff it is < K — see
+    include/fuvs.h; arg-max output never holds it.)"""
+    H, W = 48, 80
+    g = torch.Generator().manual_seed(100 * K + n)
+    labels = torch.randint(0, K, (n, H, W), generator=g, dtype=torch.uint8)
+    last = torch.randint(0, K, (H, W), generator=g, dtype=torch.uint8)
+    if foreign:
+        for i, v in enumerate((K + 1, 7, 8, 15, 16, 200, 255)):
+            labels[i % n, (3 * i) % H::11, (5 * i) % W::13] = v
+            last[(2 * i + 1) % H::9, (7 * i) % W::17] = v
     for prev in (None, last):
         ref, _ = oracle_temporal(labels.long(), K, None if prev is None else prev.numpy().astype(np.int64))
         got = kernels.temporal_counts(labels.to(cuda), K, 255, tc_prev=None if prev is None else prev.to(cuda))

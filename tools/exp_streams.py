@@ -1,7 +1,7 @@
 """Developer experiment: do independent clips on S streams fill each other's CTA tails?
 usage: python tools/exp_streams.py <mode> <nstreams> [steps]   -> us per interval (graph replay, 4 clips x 3 intervals per step)
 Granularity "clip": clip c runs on stream c % S.  FUVS_EXP_GRAN=interval: interval i of a clip on stream i % S with the
-temporal-count dependency kept by events (labels of the previous interval)."""
+temporal-count dependency kept by events (labels of the previous interval).  FUVS_EXP_NOCOUNTS=1: no temporal counts."""
 import os
 import sys
 
@@ -23,7 +23,7 @@ lib = kernels.load()
 clips = [bench.make_clip(mode, dev, i) for i in range(4)]
 need = max(bench.scratch_floats(kernels, mode), 1)
 scratch = [torch.empty((need,), dtype=torch.float32, device=dev) for _ in range(S)]
-counts = [kernels.new_counts(bench.C, dev) for _ in range(S)]
+counts = [None if os.environ.get("FUVS_EXP_NOCOUNTS") else kernels.new_counts(bench.C, dev) for _ in range(S)]
 streams = [torch.cuda.Stream(dev) for _ in range(S)]
 
 
