@@ -80,10 +80,44 @@ constexpr int NSLOT_C2 = nslot_for(2), NSLOT_C5 = nslot_for(5);   // 8, 7
 
 struct StripGeom {
   int nsx, nby, total, nslot;
-  int wl, wr;                                // relative cost of a forward-side / backward-side block (CTA partition)
-  int wedge;                                 // cost of a block of the two edge strips, in sixteenths
-  int wstart;                                // extra cost of the first block of a strip, in eighths of a block
 };
+constexpr int MAX_GRID = 255;
+struct StripPartition {
+  int b[MAX_GRID + 1];                       // CTA i owns blocks [b[i], b[i+1])
+};
+
+// CTA i of `grid` takes the blocks whose cumulative cost lies in [i, i+1) * total_cost / grid.  A block's cost is
+// side weight (step 1: the forward side also emits frame 0) x strip weight (the two strips at the image edge cost
+// ~12 % more: border clipping sends many lanes to the same column, i.e. the same shared-memory bank).  A CTA whose
+// range crosses into a new strip has to refill its whole window there: the first block of every strip carries an
+// extra cost of wstart / 8 blocks, which hands the CTA that owns it correspondingly fewer blocks.
+//   wl, wr : relative cost of a forward-side / backward-side block;  wedge : cost of an edge-strip block in sixteenths
+void strip_partition(const StripGeom& G, int grid, int wl, int wr, int wedge, int wstart, StripPartition* P) {
+  auto unit_w = [&](int u) {
+    const bool side = u >= G.nsx;
+    const int strip = side ? u - G.nsx : u;
+    const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
+    return static_cast<long long>(side ? wr : wl) * (edge ? wedge : 16);
+  };
+  auto unit_start = [&](int u) { return (static_cast<long long>(wstart) * unit_w(u)) >> 3; };
+  long long cost_all = 0;
+  for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u) + unit_start(u);
+  auto block_at = [&](long long num) {        // first block whose start cost is >= num * cost_all / grid
+    long long pos = (num * cost_all + grid - 1) / grid;
+    for (int u = 0; u < 2 * G.nsx; ++u) {
+      const long long w = unit_w(u), st = unit_start(u), cu = static_cast<long long>(G.nby) * w + st;
+      if (pos <= cu) {
+        if (pos <= 0) return u * G.nby;
+        const long long k = (pos - st + w - 1) / w;          // block k of the strip starts at cost st + k w (k >= 1)
+        return u * G.nby + static_cast<int>(k < 1 ? 1 : k);
+      }
+      pos -= cu;
+    }
+    return G.total;
+  };
+  for (int i = 0; i < grid; ++i) P->b[i] = block_at(i);
+  P->b[grid] = G.total;
+}
 struct StripMaps {
   CUtensorMap srcL, srcR;                    // planar [C][H][W] fp32, box BOXW x RB x 1 (4+1 sources: the plane of channel 4;
 };                                           // their interleaved part comes in row-wise bulk copies, see issue())
@@ -183,7 +217,7 @@ __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap,
 template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
-                   StripGeom G) {
+                   StripGeom G, const __grid_constant__ StripPartition P) {
   static_assert(!(EMIT && KEY0), "frame 0 and a completed frame never share a step here (the host routes n<=2 elsewhere)");
   static_assert(!IL || CT == 5, "the 4+1 state layout exists for C = 5");
   constexpr bool SIL = IL && !KEY0;              // the source window is 4+1: [ring row][x][4] then the plane of channel 4
@@ -206,39 +240,14 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
   const int lane = tid & 31;
   const int tx = tid & (TW - 1), ty = tid >> 7;                        // TW == 128
   const int HWi = H * W;                                               // the host guarantees C*H*W < 2^31
-  // CTA b takes the blocks whose cumulative cost lies in [b, b+1) * total_cost / grid.  A block's cost is
-  // side weight (step 1: the forward side also emits frame 0) x strip weight (the two strips at the image edge cost
-  // ~12 % more: border clipping sends many lanes to the same column, i.e. the same shared-memory bank).
-  auto unit_w = [&](int u) {
-    const bool side = u >= G.nsx;
-    const int strip = side ? u - G.nsx : u;
-    const bool edge = (G.nsx > 2) && (strip == 0 || strip == G.nsx - 1);
-    return (side ? G.wr : G.wl) * (edge ? G.wedge : 16);
-  };
-  // A CTA whose range crosses into a new strip has to refill its whole window there: the first block of every strip
-  // carries an extra cost of G.wstart / 8 blocks, which hands the CTA that owns it correspondingly fewer blocks.
-  auto unit_start = [&](int u) { return (static_cast<long long>(G.wstart) * unit_w(u)) >> 3; };
-  long long cost_all = 0;
-  for (int u = 0; u < 2 * G.nsx; ++u) cost_all += static_cast<long long>(G.nby) * unit_w(u) + unit_start(u);
-  auto block_at = [&](long long num) {        // first block whose start cost is >= num * cost_all / grid
-    long long pos = (num * cost_all + gridDim.x - 1) / gridDim.x;
-    for (int u = 0; u < 2 * G.nsx; ++u) {
-      const long long w = unit_w(u), st = unit_start(u), cu = static_cast<long long>(G.nby) * w + st;
-      if (pos <= cu) {
-        if (pos <= 0) return u * G.nby;
-        const long long k = (pos - st + w - 1) / w;          // block k of the strip starts at cost st + k w (k >= 1)
-        return u * G.nby + static_cast<int>(k < 1 ? 1 : k);
-      }
-      pos -= cu;
-    }
-    return G.total;
-  };
-  const int B0 = block_at(blockIdx.x);
-  const int B1 = (blockIdx.x + 1 == gridDim.x) ? G.total : block_at(blockIdx.x + 1);
+  // This CTA's contiguous, cost-weighted range of blocks: computed on the host (strip_partition) — on the device the
+  // two searches were ~1 500 instructions per thread in front of every step's first load.
+  const int B0 = P.b[blockIdx.x], B1 = P.b[blockIdx.x + 1];
 
   // Programmatic dependent launch: this CTA may have been scheduled while the previous kernel of the stream (the
   // step that produced our source states) is still draining.  Let our own successor do the same, set up the
   // barriers, then wait for the predecessor's memory to be complete before the first global access.
+  // (r02: triggering only 2 / 4 / 8 blocks before the CTA's end, or never, changes nothing measurable on one or two streams)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int b = 0; b < MAX_SLOTS; ++b) mbar_init(bar0 + 8u * b, 1);
@@ -302,9 +311,9 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
       return true;
     });
   };
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) issue(s);
-  }
+  // initial fill: slot s by lane 0 of warp s (one thread issuing all 7 x 9 copies back to back took ~1 us, which every
+  // CTA of every step spent before its first block)
+  if (lane == 0 && (tid >> 5) < NS) issue(tid >> 5);
   const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
   const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
   int u = U0, j0 = J00, left = B1 - B0, sb = 0, kglob = 0, released = 0;
@@ -613,12 +622,13 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.nby = (H + RB - 1) / RB;
   g.total = 2 * g.nsx * g.nby;
   g.nslot = nslot;
-  g.wl = KEY0 ? 9 : 8;                         // measured in r01 (eighths): 8 -> 244.6, 9 -> 242.7, 10 -> 245.3 us per interval
-  g.wr = 8;
-  g.wedge = 18;                                // sixteenths
-  g.wstart = 16;                               // measured in r01: 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
+  if (grid > MAX_GRID) grid = MAX_GRID;
+  // weights measured in r01: forward side of step 1 (eighths) 8 -> 244.6, 9 -> 242.7, 10 -> 245.3 us per interval; edge
+  // strips 18 sixteenths; strip start 0 -> 249.1, 16 -> 245.1, 32 -> 248.6 us
+  StripPartition part;
+  strip_partition(g, grid, KEY0 ? 9 : 8, 8, 18, 16, &part);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(THREADS);
@@ -629,7 +639,7 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, a, C, H, W, g);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, a, C, H, W, g, part);
   if (e != cudaSuccess) return set_error(FUVS_ECUDA, "fuvs_dense_interval(strip step): %s", cudaGetErrorString(e));
   count_launch();
   return FUVS_OK;
