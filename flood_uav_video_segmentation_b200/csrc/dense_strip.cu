@@ -80,6 +80,9 @@ constexpr int NSLOT_C2 = nslot_for(2), NSLOT_C5 = nslot_for(5);   // 8, 7
 
 struct StripGeom {
   int nsx, nby, total, nslot;
+#ifdef FUVS_STRIP_TIMING
+  int seq;                                   // launch number (developer build)
+#endif
 };
 constexpr int MAX_GRID = 255;
 struct StripPartition {
@@ -121,6 +124,11 @@ void strip_partition(const StripGeom& G, int grid, int wl, int wr, int wedge, in
 struct StripMaps {
   CUtensorMap srcL, srcR;                    // planar [C][H][W] fp32, box BOXW x RB x 1 (4+1 sources: the plane of channel 4;
 };                                           // their interleaved part comes in row-wise bulk copies, see issue())
+
+#ifdef FUVS_STRIP_TIMING
+__device__ long long* g_strip_timing = nullptr;      // developer build only (tools/strip_timing.py)
+int g_strip_seq = 0;
+#endif
 
 template <int... I, class F>
 __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, I...>, F&& f) {
@@ -255,7 +263,14 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     fence_barrier_init();
   }
   __syncthreads();
+#ifdef FUVS_STRIP_TIMING
+  const long long tm_start = clock64();
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef FUVS_STRIP_TIMING
+  const long long tm_wait = clock64();
+  long long tm_first = 0;
+#endif
 
   // Left edge of a strip's window.  Kept inside the image where the image is wide enough: a box that hangs over
   // the image edge is zero-filled by TMA but loads far slower, and border clipping never reads beyond the edge.
@@ -313,6 +328,8 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
   };
   // initial fill: slot s by lane 0 of warp s (one thread issuing all 7 x 9 copies back to back took ~1 us, which every
   // CTA of every step spent before its first block)
+  // (Issuing only the WIN slots of the first window here and the prefetch slots once it is complete shortens the warm-up
+  // of step 1 from 8.2 k to 7.0 k cycles and changes nothing per interval: tools/strip_timing.py.)
   if (lane == 0 && (tid >> 5) < NS) issue(tid >> 5);
   const float Wf = static_cast<float>(W), Hf = static_cast<float>(H);
   const float Wm1 = static_cast<float>(W - 1), Hm1 = static_cast<float>(H - 1);
@@ -453,6 +470,9 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
           mbar_wait(bar0 + 8u * (wrap ? b - NS : b), q0 ^ (wrap ? 1u : 0u));
         }
 
+#ifdef FUVS_STRIP_TIMING
+        if (kglob == 0) tm_first = clock64();
+#endif
         if (use_global) {
           unsigned valid = 0u;
 #pragma unroll
@@ -609,6 +629,12 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
     j0 = 0;
   }
   refill_if_last();                                // nothing left to load for this CTA: issue() ignores indices past the end
+#ifdef FUVS_STRIP_TIMING
+  if (g_strip_timing && lane == 0) {   // per warp: start, wait passed, first block's window complete, end, blocks
+    long long* o = g_strip_timing + ((static_cast<long long>(G.seq & 63) * MAX_GRID + blockIdx.x) * NWARPS + (tid >> 5)) * 5;
+    o[0] = tm_start; o[1] = tm_wait; o[2] = tm_first; o[3] = clock64(); o[4] = B1 - B0;
+  }
+#endif
 }
 
 template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
@@ -622,6 +648,9 @@ int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int 
   g.nby = (H + RB - 1) / RB;
   g.total = 2 * g.nsx * g.nby;
   g.nslot = nslot;
+#ifdef FUVS_STRIP_TIMING
+  g.seq = g_strip_seq++;
+#endif
   int grid = sm_count();                       // persistent: one CTA per SM
   if (grid > g.total) grid = g.total;
   if (grid > MAX_GRID) grid = MAX_GRID;
@@ -714,3 +743,9 @@ int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_
 }
 
 }  // namespace fuvs
+
+#ifdef FUVS_STRIP_TIMING
+extern "C" __attribute__((visibility("default"))) int fuvs_dev_set_strip_timing(long long* buf) {
+  return cudaMemcpyToSymbol(fuvs::g_strip_timing, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
