@@ -15,7 +15,7 @@ for mode in ("dense", "dense_smooth", "block", "block_clip", "linear", "linear_l
         continue
     per = collections.OrderedDict()
     for r in csv.reader(open(p)):
-        if len(r) > 14 and r[0].isdigit() and "fuvs::" in r[4]:      # torch kernels of the input generator
+        if len(r) > 14 and r[0].isdigit() and "at::" not in r[4]:    # not: torch kernels of the input generator
             per.setdefault(int(r[0]), {"name": r[4]})[r[12]] = float(r[14].replace(",", ""))
     items = list(per.values())
     half = items[len(items) // 2:]                         # second repetition: 3 intervals
