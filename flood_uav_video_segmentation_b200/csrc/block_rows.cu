@@ -30,13 +30,16 @@ constexpr int KROWS = 4;             // KLR: source rows of the decoder-resoluti
 // up-sample (F.interpolate(bilinear, align_corners=True), flow/model.py:191-193), evaluated like the chain states — the
 // horizontal two-terms of the <= KROWS source rows this CTA's output rows touch are staged once, each output row is one
 // vertical two-term.  The 41 MB full-resolution key frame is neither written by an up-sample launch nor read here.
-template <int CT, bool COUNTS, bool LOGITS, bool KLR>
+// SPEC: the reference's shape of the route (k = 5 frames per interval, 256-pixel column chunks) with both as compile-time
+// constants: the frame loop unrolls and the 20 shared-memory operands of a frame become immediate offsets of one base.
+template <int CT, bool COUNTS, bool LOGITS, bool KLR, bool SPEC>
 __global__ void __launch_bounds__(BR_THREADS, 2)
 block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst, const float* __restrict__ Rst, int H,
                   int W, int Hg, int Wg, int n, float sh, float sw, int XW, int nchunks, int rsplit,
                   uint8_t* __restrict__ labels, float* __restrict__ logits, const uint8_t* __restrict__ tc_prev,
                   unsigned long long* __restrict__ counts, int ignore_index, const BlendWeights wts, float one,
                   int hl, int wl, float shk, float swk) {
+  if (SPEC) { XW = 256; n = 5; }
   extern __shared__ __align__(16) float br_hs[];            // [p-1][side][row][c][XW], then the key-frame staging slots
   __shared__ unsigned sh24[24];
   // full-resolution key frame: [BR_THREADS][CT][4] cp.async slots; KLR: [KROWS][CT][XW] horizontal two-terms
@@ -171,7 +174,8 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
         u64 idx1[2] = {0ull, 0ull}, last[2] = {0ull, 0ull};
         unsigned s_last = 0u;
         int since_spill = 2;
-        for (int p = 1; p < n; ++p) {
+#pragma unroll
+        for (int p = 1; p < (SPEC ? 5 : n); ++p) {
           const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
           const float* hsL = br_hs + static_cast<size_t>(((p - 1) * 2 + 0) * 2) * CT * XW + xx;
           const float* hsR = br_hs + static_cast<size_t>(((p - 1) * 2 + 1) * 2) * CT * XW + xx;
@@ -331,11 +335,12 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
   int rsplit = BR_THREADS / ngroups;              // thread rows per CTA
   if (rsplit < 1) return 1;
   auto cu = reinterpret_cast<unsigned long long*>(counts);
+  const bool spec = CT == 5 && XW == 256 && n == 5;
 #define FUVS_BR(CNT_, LG_)                                                                                             \
   do {                                                                                                                 \
-    auto kern = block_rows_kernel<CT, CNT_, LG_, KLR>;                                                                 \
-    static SmemOptIn optin;                                                                                            \
-    if (!optin.ensure(kern, 110 * 1024)) return 1;                                                                     \
+    auto kern = spec ? block_rows_kernel<CT, CNT_, LG_, KLR, (CT == 5)> : block_rows_kernel<CT, CNT_, LG_, KLR, false>;  \
+    static SmemOptIn optin[2];                     /* one per kernel: the opt-in is an attribute of the function */      \
+    if (!optin[spec ? 1 : 0].ensure(kern, 110 * 1024)) return 1;                                                       \
     cudaLaunchConfig_t cfg = {};                                                                                       \
     cfg.gridDim = dim3(Hg * nchunks);                                                                                  \
     cfg.blockDim = dim3(BR_THREADS);                                                                                   \
