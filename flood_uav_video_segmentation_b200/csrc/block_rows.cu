@@ -180,7 +180,6 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
           const float* hsL = br_hs + static_cast<size_t>(((p - 1) * 2 + 0) * 2) * CT * XW + xx;
           const float* hsR = br_hs + static_cast<size_t>(((p - 1) * 2 + 1) * 2) * CT * XW + xx;
           u64 xp[2][CT];
-          u64 probe = zero2;
 #pragma unroll
           for (int c = 0; c < CT; ++c) {
             // four consecutive pixels arrive as two register pairs per LDS.128: the vertical two-term of
@@ -193,8 +192,6 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
             const u64 ba = two_term2<Nm::kUpOuter>(hl0, b0.x, hl1, b1.x, one2), bb = two_term2<Nm::kUpOuter>(hl0, b0.y, hl1, b1.y, one2);
             xp[0][c] = blend2x2(w0, fa, w1, ba, one2);
             xp[1][c] = blend2x2(w0, fb, w1, bb, one2);
-            probe = fma2_rn(xp[0][c], zero2, probe);
-            probe = fma2_rn(xp[1][c], zero2, probe);
             if (LOGITS) {
               float xs[4];
               unpack2(xp[0][c], xs[0], xs[1]);
@@ -202,15 +199,11 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
               PixIO<2>::store(logits + (static_cast<long long>(p) * CT + c) * HW + pix, xs);
             }
           }
-          float pr0, pr1;
-          unpack2(probe, pr0, pr1);
           u64 idx[2];
-          if ((pr0 == pr0) && (pr1 == pr1)) {          // x*0 is NaN iff x is Inf/NaN
-            idx[0] = argmax2f<CT>(xp[0]);
-            idx[1] = argmax2f<CT>(xp[1]);
-          } else {
-            exact_scan(xp, idx);
-          }
+          bool has_nan = false;                        // the class maxima propagate NaN (max.NaN): no separate probe
+          idx[0] = argmax2f_nan<CT>(xp[0], &has_nan);
+          idx[1] = argmax2f_nan<CT>(xp[1], &has_nan);
+          if (has_nan) exact_scan(xp, idx);
           if (labels) PixIO<2>::store_label_word(labels + static_cast<long long>(p) * HW + pix, PixIO<2>::label_word(idx));
           if (COUNTS) {
             unsigned fld[4];

@@ -60,6 +60,26 @@ __device__ __forceinline__ float max_classes(const float (&v)[CT]) {
   return m;
 }
 __device__ __forceinline__ float differs(float a, float b) { return a != b ? 1.0f : 0.0f; }
+// the same with NaN propagation: NaN if any class value is NaN (torch.max then returns the first NaN's index: exact scan)
+__device__ __forceinline__ float fmax3_nan(float a, float b, float c) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fmax2_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+template <int CT>
+__device__ __forceinline__ float max_classes_nan(const float (&v)[CT]) {
+  float m = v[0];
+  int c = 1;
+#pragma unroll
+  for (; c + 1 < CT; c += 2) m = fmax3_nan(m, v[c], v[c + 1]);
+  if (c < CT) m = fmax2_nan(m, v[c]);
+  return m;
+}
 
 // {float index of pixel 0, float index of pixel 1} of the first maximum over CT packed class values (CT >= 2)
 template <int CT>
@@ -68,6 +88,23 @@ __device__ __forceinline__ u64 argmax2f(const u64 (&x)[CT]) {
 #pragma unroll
   for (int c = 0; c < CT; ++c) unpack2(x[c], lo[c], hi[c]);
   const float mlo = max_classes<CT>(lo), mhi = max_classes<CT>(hi);
+  u64 t = pack2(differs(lo[CT - 2], mlo), differs(hi[CT - 2], mhi));
+#pragma unroll
+  for (int c = CT - 3; c >= 0; --c) {
+    const u64 nc = pack2(differs(lo[c], mlo), differs(hi[c], mhi));
+    t = fma2_rn(nc, t, nc);
+  }
+  return t;
+}
+// The same for values that may be NaN (Inf is fine: it compares like any other value): *has_nan is set when either
+// pixel holds a NaN class value — the caller then takes the exact scan — and the returned indices are meaningless.
+template <int CT>
+__device__ __forceinline__ u64 argmax2f_nan(const u64 (&x)[CT], bool* has_nan) {
+  float lo[CT], hi[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) unpack2(x[c], lo[c], hi[c]);
+  const float mlo = max_classes_nan<CT>(lo), mhi = max_classes_nan<CT>(hi);
+  *has_nan = *has_nan || (mlo != mlo) || (mhi != mhi);
   u64 t = pack2(differs(lo[CT - 2], mlo), differs(hi[CT - 2], mhi));
 #pragma unroll
   for (int c = CT - 3; c >= 0; --c) {

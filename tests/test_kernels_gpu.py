@@ -131,6 +131,39 @@ def test_block_interval(cuda, C, H, W, n):
     torch.testing.assert_close(logits.cpu(), cpu_logits, rtol=1e-4, atol=1e-4)   # torch-CPU vs torch-CUDA kernels differ
 
 
+@pytest.mark.parametrize("C,H,W,n", [(5, 272, 480, 5), (5, 272, 480, 3), (3, 64, 96, 5)])
+@pytest.mark.parametrize("lowres", [False, True])
+def test_block_interval_nan_and_inf(cuda, C, H, W, n, lowres):
+    """Key frames with NaN, +Inf and -Inf class values: a frame's arg-max takes the float-domain path unless one of its
+    class maxima is NaN (max.NaN), Inf - Inf in a blend makes NaN on the way.  torch.max semantics: the first NaN wins,
+    else the first maximum (Inf included)."""
+    if lowres:
+        hl, wl = H // 8, W // 8
+        o, o_next = keyframe_logits(C, hl, wl, 8, 0)[None], keyframe_logits(C, hl, wl, 8, 1)[None]
+    else:
+        o, o_next = keyframe_logits(C, H, W, 8, 0)[None], keyframe_logits(C, H, W, 8, 1)[None]
+    for k, (t, v) in enumerate(((o, float("nan")), (o_next, float("inf")), (o, float("-inf")), (o_next, float("nan")),
+                                (o, float("inf")), (o_next, float("-inf")))):
+        t[0, k % C, (2 * k + 1)::7, (3 * k)::5] = v
+    gl = flow_grids(H, W, n, "block", clip=8, side=0)
+    gr = flow_grids(H, W, n, "block", clip=8, side=1)
+    oc, onc = o.to(cuda), o_next.to(cuda)
+    glc, grc = [g.to(cuda) for g in gl], [g.to(cuda) for g in gr]
+    if lowres:
+        up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)      # noqa: E731
+        ref_logits = fo.predict_segmentation(ident, ident, up(oc), up(onc), glc, grc, n, False)
+        labels, logits = kernels.block_lowres_interval(oc, onc, (H, W), glc, grc, n, want_labels=True, want_logits=True)
+    else:
+        ref_logits = fo.predict_segmentation(ident, ident, oc, onc, glc, grc, n, False)
+        labels, logits = kernels.block_interval(oc, onc, glc, grc, n, want_labels=True, want_logits=True)
+    ref_labels = fo.argmax_labels(ref_logits)
+    assert bool(torch.isnan(ref_logits).any()) and bool(torch.isinf(ref_logits).any())
+    a, b = logits.reshape(-1), ref_logits.reshape(-1)
+    bad = int(((a.view(torch.int32) != b.view(torch.int32)) & ~(torch.isnan(a) & torch.isnan(b))).sum())     # any NaN equals any NaN
+    assert bad == 0, f"{bad} logits differ from torch-CUDA oracle"
+    assert torch.equal(labels.long().reshape(-1), ref_labels.reshape(-1))
+
+
 @pytest.mark.parametrize("jitter", [0.05, 0.3, 1.5])
 @pytest.mark.parametrize("C,H,W,n", [(5, 272, 480, 5), (2, 96, 256, 4), (7, 64, 132, 3)])
 def test_dense_interval_tma_path_and_large_motion(cuda, jitter, C, H, W, n):
