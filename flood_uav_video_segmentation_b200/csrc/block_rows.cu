@@ -14,6 +14,7 @@
 //            counts exactly like linear.cu.
 // Same ATen arithmetic as block.cu (up_coord / two_term policies), so results are bit-identical.
 #include <cstdlib>
+#include <type_traits>
 
 #include "fuvs_common.cuh"
 #include "pix4.cuh"
@@ -113,73 +114,91 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
     const int grp = tid % ngroups, rphase = tid / ngroups;
     if (rphase < rsplit) {
       const int xx = grp * 4;
-      for (int y = y_lo + rphase; y < y_hi; y += rsplit) {
-        const UpCoord hc = up_coord<Nm>(sh, y, Hg);
-        const u64 hl0 = pack2(hc.l0, hc.l0), hl1 = pack2(hc.l1, hc.l1);
-        const long long pix = static_cast<long long>(y) * W + x0 + xx;
+      const bool have_tc = COUNTS && tc_prev != nullptr;
+      float* kslot = key_stage + static_cast<size_t>(tid) * (CT * 4);
+      // Labels live as packed float indices {pixel 0, pixel 1}, {pixel 2, pixel 3} (pix4.cuh): the arg-max of a
+      // frame without NaN runs in the float domain, a frame with a NaN class value takes the exact scan and converts.
+      const u64 magic2 = pack2(8388608.f, 8388608.f);
+      const u64 fw2 = pack2(static_cast<float>(FC::FW), static_cast<float>(FC::FW));
+      auto fields = [&](const u64 (&idx)[2], unsigned (&fld)[4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float ml, mh;
+          unpack2(fma2_rn(idx[h], fw2, magic2), ml, mh);
+          fld[2 * h] = one_shl_wrap(__float_as_uint(ml));
+          fld[2 * h + 1] = one_shl_wrap(__float_as_uint(mh));
+        }
+      };
+      // pair (output frame idx, target frame tgt): O += fields(idx), T += s_tgt, I += fields(idx) where equal
+      auto count_pair = [&](const u64 (&idx)[2], const unsigned (&fld)[4], const u64 (&tgt)[2], unsigned s_tgt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float il, ih, tl, th;
+          unpack2(idx[h], il, ih);
+          unpack2(tgt[h], tl, th);
+          cnt.accI += (il == tl) ? fld[2 * h] : 0u;
+          cnt.accI += (ih == th) ? fld[2 * h + 1] : 0u;
+        }
+        cnt.accO += (fld[0] + fld[1]) + (fld[2] + fld[3]);
+        cnt.accT += s_tgt;
+      };
+      auto exact_scan = [&](const u64 (&xp)[2][CT], u64 (&idx)[2]) {
+        float x[CT][4];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          unpack2(xp[0][c], x[c][0], x[c][1]);
+          unpack2(xp[1][c], x[c][2], x[c][3]);
+        }
+        int lab[4];
+        argmaxN<CT, 4, true>(x, lab);
+        idx[0] = pack2(static_cast<float>(lab[0]), static_cast<float>(lab[1]));
+        idx[1] = pack2(static_cast<float>(lab[2]), static_cast<float>(lab[3]));
+      };
+      auto start_key = [&](long long pix) {      // key frame of one row -> this thread's staging slot (no registers held)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          const unsigned dsts = static_cast<unsigned>(__cvta_generic_to_shared(kslot + c * 4));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(key0 + c * HW + pix) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+
+      // R output rows per pass (rows y, y + rsplit): every row of this CTA interpolates between the SAME two source
+      // rows, so the 4 CT shared-memory operands of a frame are loaded once and serve both rows — half the LDS.128 per
+      // pixel and two independent FMA chains per thread (r02: the kernel sat on fixed-latency and short-scoreboard
+      // stalls with 4 warps per scheduler, profiles/r02_ncu_block_rows.txt).
+      auto rows = [&](auto r_, int y) {
+        constexpr int R = decltype(r_)::value;
+        u64 hl0[R], hl1[R];
+        long long pix[R];
+        unsigned tc_word[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const UpCoord hc = up_coord<Nm>(sh, y + r * rsplit, Hg);
+          hl0[r] = pack2(hc.l0, hc.l0);
+          hl1[r] = pack2(hc.l1, hc.l1);
+          pix[r] = static_cast<long long>(y + r * rsplit) * W + x0 + xx;
+          // the previous interval's last label map (target of frame 0): loaded here, used at the very end
+          tc_word[r] = have_tc ? PixIO<2>::load_labels(tc_prev + pix[r]) : 0u;
+        }
         // The key frame (frame 0) is the only operand streamed from HBM: start its copy into this thread's staging
         // slot now (cp.async, no registers held) and consume it AFTER frames 1..n-1 — the counts are sums over
         // (frame p, frame p-1) pairs, so their order is free.  (Consumed first, its load latency was the top stall.)
-        float* kslot = key_stage + static_cast<size_t>(tid) * (CT * 4);
-        // same for the previous interval's last label map (target of frame 0): loaded here, used at the very end
-        const bool have_tc = COUNTS && tc_prev != nullptr;
-        const unsigned tc_word = have_tc ? PixIO<2>::load_labels(tc_prev + pix) : 0u;
-        if (!KLR) {
+        if (!KLR) start_key(pix[0]);
+        u64 idx1[R][2], last[R][2];
+        unsigned s_last[R];
 #pragma unroll
-          for (int c = 0; c < CT; ++c) {
-            const unsigned dsts = static_cast<unsigned>(__cvta_generic_to_shared(kslot + c * 4));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(key0 + c * HW + pix) : "memory");
-          }
-          asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int r = 0; r < R; ++r) {
+          idx1[r][0] = idx1[r][1] = last[r][0] = last[r][1] = 0ull;
+          s_last[r] = 0u;
         }
-
-        // Labels live as packed float indices {pixel 0, pixel 1}, {pixel 2, pixel 3} (pix4.cuh): the arg-max of a
-        // frame without NaN runs in the float domain, a frame with NaN / Inf takes the exact scan and converts.
-        const u64 magic2 = pack2(8388608.f, 8388608.f);
-        const u64 fw2 = pack2(static_cast<float>(FC::FW), static_cast<float>(FC::FW));
-        auto fields = [&](const u64 (&idx)[2], unsigned (&fld)[4]) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float ml, mh;
-            unpack2(fma2_rn(idx[h], fw2, magic2), ml, mh);
-            fld[2 * h] = one_shl_wrap(__float_as_uint(ml));
-            fld[2 * h + 1] = one_shl_wrap(__float_as_uint(mh));
-          }
-        };
-        // pair (output frame idx, target frame tgt): O += fields(idx), T += s_tgt, I += fields(idx) where equal
-        auto count_pair = [&](const u64 (&idx)[2], const unsigned (&fld)[4], const u64 (&tgt)[2], unsigned s_tgt) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float il, ih, tl, th;
-            unpack2(idx[h], il, ih);
-            unpack2(tgt[h], tl, th);
-            cnt.accI += (il == tl) ? fld[2 * h] : 0u;
-            cnt.accI += (ih == th) ? fld[2 * h + 1] : 0u;
-          }
-          cnt.accO += (fld[0] + fld[1]) + (fld[2] + fld[3]);
-          cnt.accT += s_tgt;
-        };
-        auto exact_scan = [&](const u64 (&xp)[2][CT], u64 (&idx)[2]) {
-          float x[CT][4];
-#pragma unroll
-          for (int c = 0; c < CT; ++c) {
-            unpack2(xp[0][c], x[c][0], x[c][1]);
-            unpack2(xp[1][c], x[c][2], x[c][3]);
-          }
-          int lab[4];
-          argmaxN<CT, 4, true>(x, lab);
-          idx[0] = pack2(static_cast<float>(lab[0]), static_cast<float>(lab[1]));
-          idx[1] = pack2(static_cast<float>(lab[2]), static_cast<float>(lab[3]));
-        };
-        u64 idx1[2] = {0ull, 0ull}, last[2] = {0ull, 0ull};
-        unsigned s_last = 0u;
-        int since_spill = 2;
+        int since_spill = 2 * R;                  // in units of 4 labels
 #pragma unroll
         for (int p = 1; p < (SPEC ? 5 : n); ++p) {
           const u64 w0 = pack2(wts.w0[p], wts.w0[p]), w1 = pack2(wts.w1[p], wts.w1[p]);
           const float* hsL = br_hs + static_cast<size_t>(((p - 1) * 2 + 0) * 2) * CT * XW + xx;
           const float* hsR = br_hs + static_cast<size_t>(((p - 1) * 2 + 1) * 2) * CT * XW + xx;
-          u64 xp[2][CT];
+          u64 xp[R][2][CT];
 #pragma unroll
           for (int c = 0; c < CT; ++c) {
             // four consecutive pixels arrive as two register pairs per LDS.128: the vertical two-term of
@@ -188,48 +207,59 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
             const ulonglong2 f1 = *reinterpret_cast<const ulonglong2*>(hsL + (1 * CT + c) * XW);
             const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(hsR + (0 * CT + c) * XW);
             const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(hsR + (1 * CT + c) * XW);
-            const u64 fa = two_term2<Nm::kUpOuter>(hl0, f0.x, hl1, f1.x, one2), fb = two_term2<Nm::kUpOuter>(hl0, f0.y, hl1, f1.y, one2);
-            const u64 ba = two_term2<Nm::kUpOuter>(hl0, b0.x, hl1, b1.x, one2), bb = two_term2<Nm::kUpOuter>(hl0, b0.y, hl1, b1.y, one2);
-            xp[0][c] = blend2x2(w0, fa, w1, ba, one2);
-            xp[1][c] = blend2x2(w0, fb, w1, bb, one2);
-            if (LOGITS) {
-              float xs[4];
-              unpack2(xp[0][c], xs[0], xs[1]);
-              unpack2(xp[1][c], xs[2], xs[3]);
-              PixIO<2>::store(logits + (static_cast<long long>(p) * CT + c) * HW + pix, xs);
-            }
-          }
-          u64 idx[2];
-          bool has_nan = false;                        // the class maxima propagate NaN (max.NaN): no separate probe
-          idx[0] = argmax2f_nan<CT>(xp[0], &has_nan);
-          idx[1] = argmax2f_nan<CT>(xp[1], &has_nan);
-          if (has_nan) exact_scan(xp, idx);
-          if (labels) PixIO<2>::store_label_word(labels + static_cast<long long>(p) * HW + pix, PixIO<2>::label_word(idx));
-          if (COUNTS) {
-            unsigned fld[4];
-            fields(idx, fld);
-            if (p == 1) {
-              idx1[0] = idx[0];
-              idx1[1] = idx[1];
-            } else {
-              count_pair(idx, fld, last, s_last);
-              if (++since_spill >= FC::CAP / 4) {
-                cnt.spill();
-                since_spill = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              const u64 fa = two_term2<Nm::kUpOuter>(hl0[r], f0.x, hl1[r], f1.x, one2), fb = two_term2<Nm::kUpOuter>(hl0[r], f0.y, hl1[r], f1.y, one2);
+              const u64 ba = two_term2<Nm::kUpOuter>(hl0[r], b0.x, hl1[r], b1.x, one2), bb = two_term2<Nm::kUpOuter>(hl0[r], b0.y, hl1[r], b1.y, one2);
+              xp[r][0][c] = blend2x2(w0, fa, w1, ba, one2);
+              xp[r][1][c] = blend2x2(w0, fb, w1, bb, one2);
+              if (LOGITS) {
+                float xs[4];
+                unpack2(xp[r][0][c], xs[0], xs[1]);
+                unpack2(xp[r][1][c], xs[2], xs[3]);
+                PixIO<2>::store(logits + (static_cast<long long>(p) * CT + c) * HW + pix[r], xs);
               }
             }
-            s_last = (fld[0] + fld[1]) + (fld[2] + fld[3]);
-            last[0] = idx[0];
-            last[1] = idx[1];
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            u64 idx[2];
+            bool has_nan = false;                        // the class maxima propagate NaN (max.NaN): no separate probe
+            idx[0] = argmax2f_nan<CT>(xp[r][0], &has_nan);
+            idx[1] = argmax2f_nan<CT>(xp[r][1], &has_nan);
+            if (has_nan) exact_scan(xp[r], idx);
+            if (labels) PixIO<2>::store_label_word(labels + static_cast<long long>(p) * HW + pix[r], PixIO<2>::label_word(idx));
+            if (COUNTS) {
+              unsigned fld[4];
+              fields(idx, fld);
+              if (p == 1) {
+                idx1[r][0] = idx[0];
+                idx1[r][1] = idx[1];
+              } else {
+                count_pair(idx, fld, last[r], s_last[r]);
+                if (++since_spill >= FC::CAP / 4) {
+                  cnt.spill();
+                  since_spill = 0;
+                }
+              }
+              s_last[r] = (fld[0] + fld[1]) + (fld[2] + fld[3]);
+              last[r][0] = idx[0];
+              last[r][1] = idx[1];
+            }
           }
         }
         // frame 0: the key frame itself (flow/model.py:195-197), then the pairs (0, previous interval) and (1, 0)
-        if (!KLR) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (COUNTS && 4 * since_spill + 8 > FC::CAP) cnt.spill();       // room for the two pairs below
-        {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (!KLR) asm volatile("cp.async.wait_group 0;" ::: "memory");
+          if (COUNTS && 4 * since_spill + 8 > FC::CAP) {       // room for the two pairs below
+            cnt.spill();
+            since_spill = 0;
+          }
+          since_spill += 2;
           u64 xp[2][CT];
           if (KLR) {
-            const UpCoord kh = up_coord<Nm>(shk, y, hl);
+            const UpCoord kh = up_coord<Nm>(shk, y + r * rsplit, hl);
             const u64 kl0 = pack2(kh.l0, kh.l0), kl1 = pack2(kh.l1, kh.l1);
             const float* ka = key_stage + static_cast<size_t>((kh.i0 - kfirst) * CT) * XW + xx;
             const float* kb = ka + static_cast<size_t>(kh.ip * CT) * XW;
@@ -243,7 +273,7 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
                 float xs[4];
                 unpack2(xp[0][c], xs[0], xs[1]);
                 unpack2(xp[1][c], xs[2], xs[3]);
-                PixIO<2>::store(logits + c * HW + pix, xs);
+                PixIO<2>::store(logits + c * HW + pix[r], xs);
               }
             }
           } else {
@@ -254,19 +284,21 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
               xp[1][c] = pack2(v.z, v.w);
               if (LOGITS) {
                 const float xs[4] = {v.x, v.y, v.z, v.w};
-                PixIO<2>::store(logits + c * HW + pix, xs);
+                PixIO<2>::store(logits + c * HW + pix[r], xs);
               }
             }
           }
           u64 idx0[2];
           exact_scan(xp, idx0);
+          // the slot's values are consumed (the scan above depends on them): the next row's key frame may land in it
+          if (!KLR && r + 1 < R) start_key(pix[r + 1]);
           const unsigned w = PixIO<2>::label_word(idx0);
-          if (labels) PixIO<2>::store_label_word(labels + pix, w);
+          if (labels) PixIO<2>::store_label_word(labels + pix[r], w);
           if (COUNTS) {
             unsigned fld0[4];
             fields(idx0, fld0);
             if (have_tc) {
-              const unsigned t = tc_word;
+              const unsigned t = tc_word[r];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int tl = (t >> (8 * i)) & 255u, lab = (w >> (8 * i)) & 255u;
@@ -277,13 +309,16 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
             }
             if (n > 1) {
               unsigned fld1[4];
-              fields(idx1, fld1);
-              count_pair(idx1, fld1, idx0, (fld0[0] + fld0[1]) + (fld0[2] + fld0[3]));
+              fields(idx1[r], fld1);
+              count_pair(idx1[r], fld1, idx0, (fld0[0] + fld0[1]) + (fld0[2] + fld0[3]));
             }
           }
         }
         if (COUNTS) cnt.spill();
-      }
+      };
+      int y = y_lo + rphase;
+      for (; y + rsplit < y_hi; y += 2 * rsplit) rows(std::integral_constant<int, 2>{}, y);
+      if (y < y_hi) rows(std::integral_constant<int, 1>{}, y);
     }
   }
   if (COUNTS) cnt.finish(sh24, counts, CT);
