@@ -58,7 +58,10 @@ def algorithmic_bytes(mode, k=K_DELTA):
         hg, wg = H // 16, W // 16
         return 2 * C * (H // 8) * (W // 8) * 4 + 8 * C * hg * wg * 4 + 2 * (k - 1) * hg * wg * 8 + (k + 1) * LB_BYTES
     g = H * W * 8
-    return (5 * k - (8 if k % 2 == 0 else 7)) * S_BYTES + 2 * (k - 1) * g + (k + 1) * LB_BYTES
+    dense = (5 * k - (8 if k % 2 == 0 else 7)) * S_BYTES + 2 * (k - 1) * g + (k + 1) * LB_BYTES
+    if mode == "dense_lowres":     # + the decoder-resolution key frames in and ONE up-sampled key frame written per interval
+        return dense + S_BYTES + 2 * C * (H // 8) * (W // 8) * 4      # (the other one is the previous interval's `next`)
+    return dense
 
 
 def feature_bytes(cf, fh, fw, hg, wg, k=K_DELTA):
@@ -127,9 +130,11 @@ def make_grids(n_grids, mode, device, gen):
 def make_clip(mode, device, seed):
     """One 16-frame clip: 4 key-frame logit maps [1,C,H,W] and, per interval, stacked grids [k-1,Hg,Wg,2] x2."""
     gen = torch.Generator(device=device).manual_seed(seed)
-    lowres = mode in ("linear_lowres", "block_lowres")
+    lowres = mode in ("linear_lowres", "block_lowres", "dense_lowres")
     if mode in ("block_clip", "block_lowres"):       # same grids as "block": only the entry point / key-frame size differ
         mode = "block"
+    if mode == "dense_lowres":
+        mode = "dense"
     n_int = (CLIP_FRAMES - 1) // K_DELTA
     kh, kw = (H // 8, W // 8) if lowres else (H, W)
     keys = [torch.randn((1, C, kh, kw), device=device, generator=gen) for _ in range(n_int + 1)]
@@ -145,7 +150,7 @@ def make_clip(mode, device, seed):
 def clip_bytes(mode):
     n_int = (CLIP_FRAMES - 1) // K_DELTA
     b = (n_int + 1) * S_BYTES
-    if mode in ("dense", "dense_smooth"):
+    if mode in ("dense", "dense_smooth", "dense_lowres"):
         b += n_int * 2 * (K_DELTA - 1) * H * W * 8
     elif mode in ("block", "block_clip"):
         b += n_int * 2 * (K_DELTA - 1) * (H // 16) * (W // 16) * 8
@@ -203,6 +208,9 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- device-resident arm
+_UPS = {}
+
+
 def run_interval(kernels, mode, keys, grids, it, tc_prev, counts, scratch=None):
     if mode == "linear":
         labels, _ = kernels.linear_blend_argmax(keys[it], keys[it + 1], K_DELTA, tc_prev=tc_prev, counts=counts)
@@ -211,6 +219,11 @@ def run_interval(kernels, mode, keys, grids, it, tc_prev, counts, scratch=None):
     elif mode in ("dense", "dense_smooth"):
         labels, _ = kernels.dense_interval(keys[it], keys[it + 1], grids[it][0], grids[it][1], K_DELTA, tc_prev=tc_prev,
                                            counts=counts, scratch=scratch)
+    elif mode == "dense_lowres":
+        # one pair of up-sample buffers per stream (= per scratch buffer): an interval's `next` is the following one's `prev`
+        ups = _UPS.setdefault(scratch.data_ptr() if scratch is not None else 0, kernels.KeyFrameUps())
+        labels, _ = kernels.dense_lowres_interval(keys[it], keys[it + 1], (H, W), grids[it][0], grids[it][1], K_DELTA,
+                                                  tc_prev=tc_prev, counts=counts, scratch=scratch, ups=ups)
     elif mode == "block_lowres":
         labels, _ = kernels.block_lowres_interval(keys[it], keys[it + 1], (H, W), grids[it][0], grids[it][1], K_DELTA,
                                                   tc_prev=tc_prev, counts=counts, scratch=scratch)
@@ -235,7 +248,7 @@ def run_clip(kernels, mode, clip, counts, scratch=None):
 
 def scratch_floats(kernels, mode):
     lib = kernels.load()
-    if mode in ("dense", "dense_smooth"):
+    if mode in ("dense", "dense_smooth", "dense_lowres"):
         return int(lib.fuvs_dense_scratch_floats(C, H, W, K_DELTA))
     if mode in ("block", "block_clip", "block_lowres"):
         return 3 * int(lib.fuvs_block_scratch_floats(C, H // 16, W // 16, K_DELTA))
@@ -790,7 +803,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="dense", choices=["dense", "block", "block_clip", "block_lowres", "linear", "dense_smooth", "linear_lowres"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "block", "block_clip", "block_lowres", "linear", "dense_smooth", "linear_lowres", "dense_lowres"])
     ap.add_argument("--clips-per-step", type=int, default=40, help="40 clips = 120 intervals: a dense step is ~27 ms")
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams the independent clips of a step alternate over")
@@ -864,7 +877,7 @@ def main():
         out["single_stream"] = {"us_per_interval": ms1 * 1e3 / iv1, "achieved_gbs": a1, "frac": a1 / peak,
                                 "value": iv1 * (K_DELTA - 1) * world / (ms1 / 1e3), "unit": "frames/s"}
 
-    if rank == 0 and world == 1 and not args.no_cpu and mode not in ("linear_lowres", "block_lowres"):
+    if rank == 0 and world == 1 and not args.no_cpu and mode not in ("linear_lowres", "block_lowres", "dense_lowres"):
         # the reference's own op sequence as stock torch-CUDA kernels on the same GPU, inputs resident (context for
         # `value`: there is no Blackwell-specific reference kernel to compare with)
         n_st = 6
@@ -929,7 +942,7 @@ def main():
             del mclips
             torch.cuda.empty_cache()
 
-        for m in ("linear", "linear_lowres", "block", "block_clip", "block_lowres", "dense", "dense_smooth"):
+        for m in ("linear", "linear_lowres", "block", "block_clip", "block_lowres", "dense", "dense_smooth", "dense_lowres"):
             if m != mode:
                 measure(m, m, False, m in ("linear", "block", "dense_smooth"))
         # BASELINE.json configs[0]: data.train_w = 433 crops, beside the reference's CPU path

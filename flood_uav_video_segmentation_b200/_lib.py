@@ -40,6 +40,7 @@ SIGNATURES = {
     "fuvs_dense_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_dense_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_dense_interval_ptrs": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
+    "fuvs_dense_lowres_interval_ptrs": (_i, [_p, _p, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_scratch_floats": (_ll, [_i, _i, _i, _i]),
     "fuvs_block_interval": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "fuvs_block_interval_ptrs": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _p]),

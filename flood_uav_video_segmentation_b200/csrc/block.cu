@@ -103,6 +103,48 @@ static int launch_upsample(const float* src, float* dst, long long planes, int H
   return check_launch("fuvs_upsample_bilinear_ac");
 }
 
+// Up-sample of a 5-class key frame into the dense strip kernel's "4+1" state layout (dense_strip.cu `layout`): channels
+// 0-3 interleaved per pixel ([H][W][4]) followed by the plane of channel 4.  One thread = 4 consecutive pixels of all
+// five classes: four 128-bit stores into the interleaved part, one into the plane.  Same up_fetch<> arithmetic as
+// fuvs_upsample_bilinear_ac.
+template <class NM>
+__global__ void __launch_bounds__(256)
+upsample_bilinear_ac_il5_kernel(const float* __restrict__ src, float* __restrict__ dst, int Hin, int Win, int Hout,
+                                int Wout, float sh, float sw) {
+  const int groups = Wout >> 2;
+  const long long items = static_cast<long long>(Hout) * groups;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= items) return;
+  const int y = static_cast<int>(t / groups), x = static_cast<int>(t - static_cast<long long>(y) * groups) << 2;
+  const UpCoord hc = up_coord<NM>(sh, y, Hin);
+  UpCoord wc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wc[i] = up_coord<NM>(sw, x + i, Win);
+  const long long in_plane = static_cast<long long>(Hin) * Win, out_plane = static_cast<long long>(Hout) * Wout;
+  const long long pix = static_cast<long long>(y) * Wout + x;
+  float v[5][4];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[c][i] = up_fetch<NM>(src + c * in_plane, Win, hc, wc[i]);
+  }
+  float4* q = reinterpret_cast<float4*>(dst) + pix;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = make_float4(v[0][i], v[1][i], v[2][i], v[3][i]);
+  *reinterpret_cast<float4*>(dst + 4 * out_plane + pix) = make_float4(v[4][0], v[4][1], v[4][2], v[4][3]);
+}
+
+// Key frame [C,hl,wl] -> [C,H,W] (F.interpolate bilinear, align_corners=True; flow/model.py:191-193), planar or 4+1.
+int launch_upsample_keyframe(const float* src, float* dst, int C, int hl, int wl, int H, int W, bool il, cudaStream_t st) {
+  if (!il) return launch_upsample<Nm>(src, dst, C, hl, wl, H, W, st);
+  if (C != 5 || (W & 3) != 0 || !aligned16(dst) || static_cast<long long>(H) * W >= (1ll << 31))
+    return set_error(FUVS_EINVAL, "up-sample into the 4+1 layout needs C = 5, W %% 4 == 0 and a 16-byte aligned destination");
+  const long long items = (static_cast<long long>(H) * W) >> 2;
+  const long long bx = (items + 255) / 256;
+  upsample_bilinear_ac_il5_kernel<Nm><<<static_cast<unsigned>(bx), 256, 0, st>>>(src, dst, hl, wl, H, W, ac_scale(hl, H), ac_scale(wl, W));
+  return check_launch("fuvs_dense_lowres_interval(up-sample)");
+}
+
 // ---------------------------------------------------------------------------
 // block-grid chain step (low resolution): one launch advances both chains of up to CHAIN_MAX_IV intervals by one step
 // (blockIdx.z = 2 * interval + side).  A clip's intervals are independent until their label maps meet in the

@@ -22,6 +22,8 @@ struct DenseStep {
   // 1: the chain states of this interval (dst*, point*, and src* unless key0 is set) are stored "4+1" — channels 0-3
   // interleaved per pixel ([H][W][4]) followed by the plane of channel 4 (C = 5, strip kernel only, dense_strip.cu)
   int il;
+  // 1: step 1 of a 4+1 interval whose key frames (srcL, srcR, key0) are 4+1 themselves (fuvs_dense_lowres_interval)
+  int key_il;
 };
 
 // dense_tma.cu: returns FUVS_OK if it ran the step, 1 if the shape is not eligible (caller uses the direct kernel),
@@ -33,5 +35,8 @@ int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_
 // true if every step of the interval can run on the strip kernel with 4+1 chain states (decided once per interval)
 bool dense_strip_il_ok(int C, int H, int W, int n, const float* prev, const float* next, const float* gridsL,
                        const float* gridsR, const float* scratch);
+
+// block.cu: key frame [C,hl,wl] -> [C,H,W] (bilinear, align_corners=True), planar or 4+1 (C = 5)
+int launch_upsample_keyframe(const float* src, float* dst, int C, int hl, int wl, int H, int W, bool il, cudaStream_t st);
 
 }  // namespace fuvs

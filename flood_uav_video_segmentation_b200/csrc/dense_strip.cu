@@ -206,7 +206,7 @@ __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap,
         if (logit_out) __stcs(logit_out + o, v);
       }
       if (key0) {
-        const float v = __ldg(A.key0 + o);
+        const float v = __ldg(A.key0 + state_index(il_src, c, pix, HW));
         am0.push(v, c);
         if (A.logit0) __stcs(A.logit0 + o, v);
       }
@@ -222,13 +222,15 @@ __device__ __noinline__ void block_from_global(const DenseStep* __restrict__ Ap,
 //   FULLV  : W % 128 == 0 and H % 8 == 0: every pixel of every block exists
 //   NSC    : ring slots when known at compile time (0: G.nslot)
 //   IL     : C = 5 only: the states of this interval (dst, pointwise operand, and the source unless KEY0) are 4+1
-template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
+//   KIL    : KEY0 and IL: the key frames themselves are 4+1 (written so by fuvs_dense_lowres_interval's up-sample)
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL, bool KIL>
 __global__ void __launch_bounds__(THREADS, 1)
 dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ DenseStep A, int Crt, int H, int W,
                    StripGeom G, const __grid_constant__ StripPartition P) {
   static_assert(!(EMIT && KEY0), "frame 0 and a completed frame never share a step here (the host routes n<=2 elsewhere)");
   static_assert(!IL || CT == 5, "the 4+1 state layout exists for C = 5");
-  constexpr bool SIL = IL && !KEY0;              // the source window is 4+1: [ring row][x][4] then the plane of channel 4
+  static_assert(!KIL || (KEY0 && IL), "4+1 key frames belong to step 1 of a 4+1 interval");
+  constexpr bool SIL = IL && (!KEY0 || KIL);     // the source window is 4+1: [ring row][x][4] then the plane of channel 4
   constexpr int CR = CT > 0 ? CT : 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int C = CT > 0 ? CT : Crt;
@@ -489,7 +491,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
             for (int r = 0; r < PX; ++r) {
               unsigned rr = static_cast<unsigned>(rb0 + HALO_Y + ty + r * TROWS);
               rr = min(rr, rr - static_cast<unsigned>(NSR));
-              akey[r] = colbase + rr * (BOXW * 4u);
+              akey[r] = SIL ? rr * BOXW + (colbase - ring0) / 4u : colbase + rr * (BOXW * 4u);   // 4+1: element index
             }
           }
           ArgMax am[PX];
@@ -531,10 +533,16 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
             if (KEY0 && do_key0) {
               static_for<PX>([&](auto r_) {
                 constexpr int r = decltype(r_)::value;
-                static_for<CT>([&](auto c_) {
-                  constexpr int c = decltype(c_)::value;
-                  vk[r][c] = lds_imm<c * CHB>(akey[r]);
-                });
+                if constexpr (SIL) {
+                  const float4 t = lds4_imm<0>(ring0 + akey[r] * 16u);
+                  vk[r][0] = t.x; vk[r][1] = t.y; vk[r][2] = t.z; vk[r][3] = t.w;
+                  vk[r][CT - 1] = lds_imm<0>(ring0 + 4u * CHB + akey[r] * 4u);
+                } else {
+                  static_for<CT>([&](auto c_) {
+                    constexpr int c = decltype(c_)::value;
+                    vk[r][c] = lds_imm<c * CHB>(akey[r]);
+                  });
+                }
               });
             }
             // ---- FMA chains in ATen's order (nw, ne, sw, se; neighbours outside the image are skipped), stores, blends
@@ -637,10 +645,10 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
 #endif
 }
 
-template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL>
+template <int CT, int NSC, bool EMIT, bool KEY0, bool WDST, bool FULLV, bool IL, bool KIL = false>
 int launch_variant(const StripMaps& maps, const DenseStep& a, int C, int H, int W, int nslot, cudaStream_t st) {
   static SmemOptIn optin;
-  auto kern = dense_strip_kernel<CT, NSC, EMIT, KEY0, WDST, FULLV, IL>;
+  auto kern = dense_strip_kernel<CT, NSC, EMIT, KEY0, WDST, FULLV, IL, KIL>;
   const size_t smem = static_cast<size_t>(nslot) * C * PLANE * 4 + 256;
   if (!optin.ensure(kern, SMEM_LIMIT)) return set_error(FUVS_ECUDA, "fuvs_dense_interval(strip step): shared-memory opt-in failed");
   StripGeom g;
@@ -680,6 +688,9 @@ int launch_ct(const StripMaps& maps, const DenseStep& a, int C, int H, int W, in
   if (a.emitA) {
     return wdst ? launch_variant<CT, NSC, true, false, true, FULLV, IL>(maps, a, C, H, W, nslot, st)
                 : launch_variant<CT, NSC, true, false, false, FULLV, IL>(maps, a, C, H, W, nslot, st);
+  }
+  if constexpr (IL) {
+    if (a.key0 && a.key_il) return launch_variant<CT, NSC, false, true, true, FULLV, IL, true>(maps, a, C, H, W, nslot, st);
   }
   if (a.key0) return launch_variant<CT, NSC, false, true, true, FULLV, IL>(maps, a, C, H, W, nslot, st);
   return launch_variant<CT, NSC, false, false, true, FULLV, IL>(maps, a, C, H, W, nslot, st);
@@ -727,7 +738,8 @@ int launch_dense_step_strip(const DenseStep& a, int C, int H, int W, cudaStream_
   if (a.il && C != 5) return ineligible();
   const int nslot = nslot_for(C);
   StripMaps maps;
-  const bool sil = a.il && !a.key0;
+  if (a.key_il && !(a.il && a.key0)) return ineligible();
+  const bool sil = a.il && (!a.key0 || a.key_il);
   const long long HW = static_cast<long long>(H) * W;
   if (sil) {
     // 4+1 source: channels 0-3 interleaved, channel 4 a plane behind them

@@ -206,11 +206,15 @@ extern "C" int fuvs_dense_interval(const float* prev, const float* next, const f
   return fuvs_dense_interval_ptrs(prev, next, gl, gr, C, H, W, n, scratch, labels, logits, tc_prev, counts, ignore_index, stream);
 }
 
-extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, const float* const* grids_left,
-                                        const float* const* grids_right, int C, int H, int W, int n, float* scratch,
-                                        uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
-                                        int ignore_index, fuvs_stream_t stream) {
-  using namespace fuvs;
+namespace fuvs {
+// lowres: 0 = prev / next are full-resolution planar key frames (fuvs_dense_interval);
+//         1 = they are caller-owned buffers that receive the up-sample of prev_lr / next_lr [C,hl,wl] first
+//             (fuvs_dense_lowres_interval; prev_ready: prev already holds it), 4+1 when the interval runs 4+1
+static int dense_interval_impl(const float* prev, const float* next, const float* const* grids_left,
+                               const float* const* grids_right, int C, int H, int W, int n, float* scratch,
+                               uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
+                               int ignore_index, fuvs_stream_t stream, int lowres, const float* prev_lr,
+                               const float* next_lr, int hl, int wl, int prev_ready) {
   if (int e = device_ok()) return e;
   if (!prev || C < 1 || H < 1 || W < 1 || n < 1) return set_error(FUVS_EINVAL, "dense: bad shape C=%d H=%d W=%d n=%d", C, H, W, n);
   if (n > FUVS_MAX_FRAMES) return set_error(FUVS_EINVAL, "dense: n=%d exceeds %d frames per interval", n, FUVS_MAX_FRAMES);
@@ -226,6 +230,19 @@ extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, co
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long S = static_cast<long long>(C) * HW;
+  // C = 5 with odd n keeps its chain states in the strip kernel's 4+1 layout; that is decided here, once, because a
+  // state written 4+1 must be read 4+1 (only when frames are emitted: step 1 is then the key-frame variant)
+  const bool il = n > 1 && (labels || logits) &&
+                  dense_strip_il_ok(C, H, W, n, prev, next, grids_left[0], grids_right[0], scratch);
+  if (lowres) {
+    // flow/model.py:191-193, 205-206: the decoder output up-sampled to the frame size, straight into the layout step 1 reads
+    if (!prev_ready) {
+      if (int e = launch_upsample_keyframe(prev_lr, const_cast<float*>(prev), C, hl, wl, H, W, il, st)) return e;
+    }
+    if (n > 1) {
+      if (int e = launch_upsample_keyframe(next_lr, const_cast<float*>(next), C, hl, wl, H, W, il, st)) return e;
+    }
+  }
 
   if (n == 1) {
     if (labels) {
@@ -243,7 +260,6 @@ extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, co
     // cannot take fall through to the next one.  C = 5 with odd n keeps its chain states in the strip kernel's 4+1
     // layout; that is decided here, once, because a state written 4+1 must be read 4+1.
     // (only when frames are emitted: step 1 is then the key-frame variant, the one that reads a planar source)
-    const bool il = (labels || logits) && dense_strip_il_ok(C, H, W, n, prev, next, grids_left[0], grids_right[0], scratch);
     float* Lst = scratch;                       // states 1..n-2
     float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
     for (int j = 1; j <= n - 1; ++j) {
@@ -276,6 +292,7 @@ extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, co
         a.logit0 = logits;
       }
       a.il = il ? 1 : 0;
+      a.key_il = (il && lowres && j == 1) ? 1 : 0;
       int r = launch_dense_step_strip(a, C, H, W, st);
       if (r > 0) r = launch_dense_step_tma(a, C, H, W, st);
       if (r < 0) return r;
@@ -286,4 +303,28 @@ extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, co
   }
   if (counts) return launch_temporal_counts(labels, n, HW, tc_prev, C, ignore_index, counts, st);
   return FUVS_OK;
+}
+}  // namespace fuvs
+
+extern "C" int fuvs_dense_interval_ptrs(const float* prev, const float* next, const float* const* grids_left,
+                                        const float* const* grids_right, int C, int H, int W, int n, float* scratch,
+                                        uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts,
+                                        int ignore_index, fuvs_stream_t stream) {
+  return fuvs::dense_interval_impl(prev, next, grids_left, grids_right, C, H, W, n, scratch, labels, logits, tc_prev, counts,
+                                   ignore_index, stream, 0, nullptr, nullptr, 0, 0, 0);
+}
+
+extern "C" int fuvs_dense_lowres_interval_ptrs(const float* prev_lr, const float* next_lr, int hl, int wl, float* prev_up,
+                                               int prev_up_ready, float* next_up, const float* const* grids_left,
+                                               const float* const* grids_right, int C, int H, int W, int n,
+                                               float* scratch, uint8_t* labels, float* logits, const uint8_t* tc_prev,
+                                               long long* counts, int ignore_index, fuvs_stream_t stream) {
+  using namespace fuvs;
+  if (!prev_lr || !prev_up || hl < 1 || wl < 1 || C < 1)
+    return set_error(FUVS_EINVAL, "dense_lowres: bad key frame C=%d %dx%d (prev_lr / prev_up NULL?)", C, hl, wl);
+  if (n > 1 && (!next_lr || !next_up)) return set_error(FUVS_EINVAL, "dense_lowres: next_lr / next_up are NULL but n=%d", n);
+  if (prev_up == next_up) return set_error(FUVS_EINVAL, "dense_lowres: prev_up and next_up must be different buffers");
+  if (static_cast<long long>(C) * hl * wl >= (1ll << 31)) return set_error(FUVS_EINVAL, "dense_lowres: key frame exceeds 2^31 elements");
+  return dense_interval_impl(prev_up, next_up, grids_left, grids_right, C, H, W, n, scratch, labels, logits, tc_prev, counts,
+                             ignore_index, stream, 1, prev_lr, next_lr, hl, wl, prev_up_ready);
 }

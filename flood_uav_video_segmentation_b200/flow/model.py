@@ -80,6 +80,7 @@ class FlowModel(nn.Module):
         self._kf_version = 0
         # chain-state workspace of the interval kernels, grown on demand and reused across calls
         self._scratch = kernels.ScratchCache()
+        self._dense_ups = kernels.KeyFrameUps()     # up-sampled key frames of the dense route (reused interval to interval)
 
     # ------------------------------------------------------------------ forward (train / val / test)
     def forward(self, frame_current, frame_prev, frame_next, mvs_left, mvs_right, left_index, right_index):
@@ -197,6 +198,8 @@ class FlowModel(nn.Module):
     def reset_keyframe_cache(self):
         self._kf_cache = None
         self._kf_version += 1
+        if hasattr(self, "_dense_ups"):
+            self._dense_ups.reset()
 
     # anything that changes the weights or the mode invalidates cached network outputs
     def train(self, mode=True):
@@ -213,9 +216,10 @@ class FlowModel(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def _keeps_lowres(self, mvs_left, h, w):
-        """Routes whose kernels evaluate the key frames' up-sample themselves: linear and
-        block-grid.  The dense route samples the full-resolution key frames through its TMA window."""
-        return self._interval_mode(mvs_left, h, w) in ("linear", "block")
+        """Routes whose entries take the key frames at decoder resolution: linear and block-grid
+        evaluate the up-sample inside their kernels, the dense entry up-samples straight into the layout its first
+        warp step reads and keeps the result for the next interval."""
+        return self._interval_mode(mvs_left, h, w) in ("linear", "block", "dense")
 
     def _interval_mode(self, mvs_left, h, w):
         if self.no_warp or len(mvs_left) == 0 or not _is_grid(mvs_left[0]):
@@ -248,7 +252,10 @@ class FlowModel(nn.Module):
             # key frames still at decoder resolution: the block route evaluates their up-sample inside its kernels
             # (shapes it does not take are up-sampled by the wrapper: same arithmetic)
             return kernels.block_lowres_interval(o, o_next, (h, w), mvs_left, mvs_right, n, scratch=self._scratch, **kw)
-        if (o.shape[2], o.shape[3]) != (h, w):                # the dense route consumes full-resolution key frames
+        if mode == "dense" and (o.shape[2], o.shape[3]) != (h, w):
+            return kernels.dense_lowres_interval(o, o_next, (h, w), mvs_left, mvs_right, n, scratch=self._scratch,
+                                                 ups=self._dense_ups, **kw)
+        if (o.shape[2], o.shape[3]) != (h, w):
             o = _interp_ac(o, h, w)
             o_next = _interp_ac(o_next, h, w) if o_next is not None else None
         if mode == "dense":

@@ -175,6 +175,75 @@ def dense_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, w
     return labels, logits
 
 
+class KeyFrameUps:
+    """The two caller-owned buffers of fuvs_dense_lowres_interval_ptrs (up-sampled key frames, library-private layout) and
+    the bookkeeping of which decoder-resolution key frame each one holds, so that an interval's `next` is reused as the
+    following interval's `prev` (flow/model.py:189,202 would up-sample it twice)."""
+
+    def __init__(self):
+        self.bufs = [None, None]
+        self.tags = [None, None]
+
+    def _buffer(self, i, numel, dev):
+        b = self.bufs[i]
+        if b is None or b.numel() != numel or b.device != dev:
+            self.bufs[i] = torch.empty((numel,), dtype=torch.float32, device=dev)
+            self.tags[i] = None
+        return self.bufs[i]
+
+    def reset(self):
+        self.tags = [None, None]
+
+
+def _keyframe_tag(t, size, n, outputs):
+    # the tensor OBJECT (kept alive, so its storage cannot be handed to another tensor) and its version counter
+    return (t, t._version, tuple(size), n, outputs)
+
+
+def _same_tag(a, b):
+    return a is not None and b is not None and a[0] is b[0] and a[1:] == b[1:]
+
+
+def dense_lowres_interval(prev_lr, nxt_lr, size, grids_left, grids_right, n, *, want_labels=True, want_logits=False,
+                          tc_prev=None, counts=None, ignore_index=255, scratch=None, ups=None):
+    """fuvs_dense_lowres_interval_ptrs: key frames at decoder resolution [C,hl,wl] / [1,C,hl,wl], frame size `size`.
+    ups: a KeyFrameUps that lives across the intervals of a clip (None: buffers allocated per call, nothing reused): when
+    prev_lr is the very tensor (same storage, same version) that was `nxt_lr` of the previous call, its up-sample is
+    reused instead of recomputed."""
+    dev = require_cuda(prev_lr, nxt_lr, tc_prev, counts, what="dense_lowres_interval")
+    prev_obj, next_obj = prev_lr, nxt_lr
+    prev_lr = _f32c(prev_lr, "prev_lr")
+    C, hl, wl = prev_lr.shape[-3:]
+    H, W = int(size[0]), int(size[1])
+    gl = gr = None
+    if n > 1:
+        nxt_lr = _f32c(nxt_lr, "next_lr")
+        if tuple(nxt_lr.shape[-3:]) != (C, hl, wl):
+            raise FuvsError("dense_lowres_interval: the two key frames differ in shape")
+        gl = _grid_list(grids_left, n, (H, W), dev, "dense_lowres_interval(grids_left)")
+        gr = _grid_list(grids_right, n, (H, W), dev, "dense_lowres_interval(grids_right)")
+    scratch = _scratch(scratch, int(load().fuvs_dense_scratch_floats(C, H, W, n)), dev)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if (want_labels or counts is not None) else None
+    logits = torch.empty((n, C, H, W), dtype=torch.float32, device=dev) if want_logits else None
+    _check_tc(tc_prev, counts, H, W, C)
+    ups = ups if ups is not None else KeyFrameUps()
+    outputs = (labels is not None, logits is not None)
+    tag_prev = _keyframe_tag(prev_obj, (H, W), n, outputs)
+    ip = 1 if _same_tag(ups.tags[1], tag_prev) else 0
+    numel = C * H * W
+    up_prev = ups._buffer(ip, numel, dev)                 # (a re-allocated buffer loses its tag)
+    ready = 1 if _same_tag(ups.tags[ip], tag_prev) else 0
+    up_next = ups._buffer(1 - ip, numel, dev)
+    with torch.cuda.device(dev):
+        check(load().fuvs_dense_lowres_interval_ptrs(ptr(prev_lr), ptr(nxt_lr) if n > 1 else None, hl, wl, ptr(up_prev), ready,
+                                                     ptr(up_next), ptr_array(gl), ptr_array(gr), C, H, W, n, ptr(scratch),
+                                                     ptr(labels), ptr(logits), ptr(tc_prev), ptr(counts), ignore_index,
+                                                     stream_ptr(dev)))
+    ups.tags[ip] = tag_prev
+    ups.tags[1 - ip] = _keyframe_tag(next_obj, (H, W), n, outputs) if n > 1 else None
+    return labels, logits
+
+
 def block_interval(prev, nxt, grids_left, grids_right, n, *, want_labels=True, want_logits=False, tc_prev=None,
                    counts=None, ignore_index=255, scratch=None):
     """fuvs_block_interval_ptrs.  grids_*: list of n-1 [1,Hg,Wg,2] tensors or stacked [n-1,Hg,Wg,2]."""

@@ -161,6 +161,27 @@ FUVS_API int fuvs_dense_interval_ptrs(const float* prev, const float* next,
                         uint8_t* labels, float* logits,
                         const uint8_t* tc_prev, long long* counts,
                         int ignore_index, fuvs_stream_t stream);
+/* Dense-flow interval with the key frames given at DECODER resolution: the
+ * F.interpolate(decoder output, size=(h,w), mode="bilinear", align_corners=True) of flow/model.py:191-193, 205-206
+ * runs inside the call and writes each up-sampled key frame straight into the layout the first warp step reads
+ * (for C = 5 and odd n the strip kernel's channel-interleaved layout: its step 1 then gathers with a quarter of the
+ * shared-memory loads), so the planar full-resolution key frame is never materialised.
+ *   prev_lr, next_lr : [C,hl,wl] decoder outputs of the two key frames
+ *   prev_up, next_up : caller-owned device buffers of C*H*W floats each (16-byte aligned), DIFFERENT buffers; they
+ *                      receive the up-sampled key frames in a layout private to the library
+ *   prev_up_ready    : != 0: prev_up already holds the up-sample of prev_lr, written as `next_up` by the previous
+ *                      interval's call with the same C, H, W, n and the same outputs requested (key-frame reuse: the
+ *                      interval's `next` is the following interval's `prev`, flow/model.py:189,202); 0: computed here
+ *   everything else  : as in fuvs_dense_interval_ptrs (scratch: fuvs_dense_scratch_floats(C,H,W,n))
+ * Results are bit-identical to fuvs_upsample_bilinear_ac on both key frames followed by fuvs_dense_interval. */
+FUVS_API int fuvs_dense_lowres_interval_ptrs(const float* prev_lr, const float* next_lr, int hl, int wl,
+                        float* prev_up, int prev_up_ready, float* next_up,
+                        const float* const* grids_left_host, const float* const* grids_right_host,
+                        int C, int H, int W, int n,
+                        float* scratch,
+                        uint8_t* labels, float* logits,
+                        const uint8_t* tc_prev, long long* counts,
+                        int ignore_index, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Macro-block-grid interval (reference-faithful: grids are [Hg,Wg,2] with

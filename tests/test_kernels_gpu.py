@@ -687,3 +687,50 @@ def test_block_lowres_interval(cuda, C, hl, wl, H, W, n):
     assert np.array_equal(counts.cpu().numpy(), ref_counts)
     labels2, none = kernels.block_lowres_interval(o_lr, o_next_lr, (H, W), gl, gr, n)
     assert none is None and torch.equal(labels2, labels)
+
+
+@pytest.mark.parametrize("C,hl,wl,H,W,n", [(5, 135, 240, 1080, 1920, 5), (5, 34, 60, 272, 480, 5), (5, 17, 32, 136, 256, 3),
+                                           (5, 17, 30, 136, 240, 4), (2, 17, 32, 136, 256, 5), (5, 20, 25, 77, 101, 3),
+                                           (7, 12, 16, 96, 128, 3), (5, 17, 32, 136, 256, 1), (5, 64, 96, 64, 96, 3)])
+def test_dense_lowres_interval(cuda, C, hl, wl, H, W, n):
+    """Dense route with the key frames at decoder resolution: the up-sample runs inside the entry
+    and, for C = 5 with odd n, writes the strip kernel's 4+1 layout that step 1 then reads.  Labels, logits and counts
+    bit-exact against F.interpolate + the reference sequence on torch-CUDA; even n, C != 5, W % 4 != 0 and n = 1 take
+    the planar route; the second interval of a clip reuses the up-sample of its `prev` (the first one's `next`)."""
+    g = torch.Generator().manual_seed(C * 1000 + hl + n)
+    keys_lr = [(torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda) for _ in range(3)]
+    up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)      # noqa: E731
+    ups = kernels.KeyFrameUps()
+    scratch = kernels.ScratchCache()
+    tc_prev = torch.randint(0, C, (H, W), generator=torch.Generator().manual_seed(5), dtype=torch.uint8).to(cuda)
+    for it in range(2):
+        o_lr, o_next_lr = keys_lr[it], keys_lr[it + 1]
+        gl = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=7 + it, side=0)]
+        gr = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=7 + it, side=1)]
+        if n > 1:
+            ref_logits = fo.predict_segmentation(ident, ident, up(o_lr), up(o_next_lr), gl, gr, n, no_warp=False)
+        else:
+            ref_logits = up(o_lr)
+        ref_labels = fo.argmax_labels(ref_logits)
+        counts = kernels.new_counts(C, cuda)
+        labels, logits = kernels.dense_lowres_interval(o_lr, o_next_lr if n > 1 else None, (H, W), gl, gr, n, want_labels=True,
+                                                       want_logits=True, tc_prev=tc_prev, counts=counts, ups=ups,
+                                                       scratch=scratch)
+        bad = int((logits.reshape(-1).view(torch.int32) != ref_logits.reshape(-1).view(torch.int32)).sum())
+        assert bad == 0, f"interval {it}: {bad} logits differ from F.interpolate + the reference sequence"
+        assert torch.equal(labels.long().reshape(-1), ref_labels.reshape(-1))
+        ref_counts, _ = oracle_temporal(ref_labels.reshape(n, H, W), C, tc_prev.cpu().numpy().astype(np.int64))
+        assert np.array_equal(counts.cpu().numpy(), ref_counts)
+        if n > 1:
+            assert ups.tags[0] is not None and ups.tags[1] is not None
+            if it == 1:      # the first interval's `next` was found again as this interval's `prev`
+                assert any(t[0] is o_lr for t in ups.tags)
+        tc_prev = labels[n - 1]
+    # a key frame changed in place is up-sampled again (version counter), labels-only calls agree
+    if n > 1:
+        keys_lr[2].mul_(-1.0)
+        gl = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=3, side=0)]
+        gr = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=3, side=1)]
+        ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, up(keys_lr[2]), up(keys_lr[0]), gl, gr, n, no_warp=False))
+        labels, none = kernels.dense_lowres_interval(keys_lr[2], keys_lr[0], (H, W), gl, gr, n, ups=ups, scratch=scratch)
+        assert none is None and torch.equal(labels.long().reshape(-1), ref.reshape(-1))

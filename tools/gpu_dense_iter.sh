@@ -1,6 +1,4 @@
 # developer loop for the dense strip kernel: parity tests, then us per interval with 1 and 2 streams
-set -x
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_golden_gpu.py tests/test_flowmodel_gpu.py -x -q -m gpu -k "dense or 1080p or graph or golden or flow" > gpurun_out/dense_tests.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/dense_tests.log
-for m in dense dense_smooth; do for s in 1 2; do timeout 200 python tools/exp_streams.py $m $s 30; done; done 2>&1 | grep streams
-if [ -f flood_uav_video_segmentation_b200/lib/libfuvs_tm.so ]; then timeout 300 python tools/strip_timing.py dense 2; fi
+for m in dense dense_lowres dense_smooth; do for s in 1 2; do timeout 200 python tools/exp_streams.py $m $s 30; done; done 2>&1 | grep "streams\|Error"
