@@ -290,7 +290,11 @@ def test_argmax_ties_and_nan(cuda):
 
 
 @pytest.mark.parametrize("shape", [((5, 67, 120), (1072, 1920)), ((3, 55, 55), (433, 433)), ((2, 9, 7), (10, 8)),
-                                   ((4, 33, 33), (33, 33)), ((2, 1, 1), (5, 7)), ((2, 6, 6), (1, 1))])
+                                   ((4, 33, 33), (33, 33)), ((2, 1, 1), (5, 7)), ((2, 6, 6), (1, 1)),
+                                   # the staged separable kernel (ratio >= 4, Wout % 4 == 0): ragged chunks, several plane chunks
+                                   ((5, 135, 240), (1080, 1920)), ((8, 17, 25), (40, 52)), ((20, 34, 60), (68, 120)),
+                                   ((2, 2, 3), (9, 8)), ((3, 7, 300), (33, 700)), ((1, 1, 6), (8, 12)),
+                                   ((20, 6, 10), (25, 44)), ((9, 5, 70), (41, 520))])
 def test_upsample(cuda, shape):
     (C, Hin, Win), (Ho, Wo) = shape
     x = torch.randn(2, C, Hin, Win, generator=torch.Generator().manual_seed(9)).to(cuda)
