@@ -402,11 +402,26 @@ def time_feature(kernels, cf, device, reps=6):
 
 
 # ----------------------------------------------------------------------------- end-to-end arm (host buffers)
-def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
-    """FlowBaseModel.predict_step with pinned HOST inputs.  Per interval the copy stream uploads the NEXT key frame's
-    logits and the 2(k-1) grids (the previous interval's `next` becomes this interval's `prev` on the device: each
-    key frame crosses PCIe once per clip), double-buffered against compute; the uint8 label maps go back D2H per
-    interval and the counts are read once at the end."""
+class Stride8Net(torch.nn.Module):
+    """Stand-in key-frame network of the end-to-end arm: stride-8 "encoder" (8x8 average pooling of the RGB frame) and a
+    random-init 1x1 "decoder" to C classes — the shapes the reference's networks produce (decoder output at 1/8 of the
+    frame, flow/model.py:188-193) at a cost that leaves the arm measuring the interpolation path."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(1234)
+        self.encoder = torch.nn.AvgPool2d(8)
+        self.decoder = torch.nn.Conv2d(3, C, 1)
+
+
+def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips, inputs="logits"):
+    """FlowBaseModel.predict_step with pinned HOST inputs.  Per interval the copy stream uploads the NEXT key frame
+    and the 2(k-1) grids (the previous interval's `next` becomes this interval's `prev` on the device: each key frame
+    crosses PCIe once per clip), double-buffered against compute; the uint8 label maps go back D2H per interval and
+    the counts are read once at the end.  inputs = "logits": the key frames are full-resolution logit maps [1,C,H,W]
+    and the network is the identity (r01's arm); "image": they are RGB frames [1,3,H,W] like the reference's batches
+    (flow/dataset.py), a stride-8 stand-in network produces decoder-resolution logits and the interval entry takes them
+    from there."""
     from flood_uav_video_segmentation_b200.flow.base import FlowBaseModel
 
     class Identity(torch.nn.Module):
@@ -415,15 +430,19 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
             self.encoder = torch.nn.Identity()
             self.decoder = torch.nn.Identity()
 
+    image = inputs == "image"
+    KC = 3 if image else C                       # channels of an uploaded key frame
+    key_bytes = KC * H * W * 4
+    backbone = (Stride8Net().to(device).eval() if image else Identity())
     model = FlowBaseModel(classes=C, arch="pspnet", feature_based=False, no_warp=(mode == "linear"), no_cropping=True,
-                          backbone=Identity(), output_size=(H, W), save_video=False)
+                          backbone=backbone, output_size=(H, W), save_video=False).eval()
     copy_stream = torch.cuda.Stream(device)
     n_int = (CLIP_FRAMES - 1) // K_DELTA
     # key-frame ring of 4 device buffers handed out round-robin: while interval j computes on two of them the copy
     # stream fills the one or two (clip boundary) that interval j+1 needs; a buffer is rewritten 4 uploads later, when
     # the last interval that read it has long been enqueued (its key_free event is recorded before the wait is issued)
     NK = 4
-    keys_dev = [torch.empty((1, C, H, W), device=device) for _ in range(NK)]
+    keys_dev = [torch.empty((1, KC, H, W), device=device) for _ in range(NK)]
     key_ready = [torch.cuda.Event() for _ in range(NK)]
     key_free = [torch.cuda.Event() for _ in range(NK)]
     gslots = []
@@ -444,7 +463,7 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
         copy_stream.wait_event(key_free[k])
         keys_dev[k].copy_(host_key, non_blocking=True)
         key_ready[k].record(copy_stream)
-        state["h2d"] += S_BYTES
+        state["h2d"] += key_bytes
         return k
 
     def stage(j, clip, it):
@@ -488,7 +507,8 @@ def time_e2e(mode, steps, warmup, clips_per_step, device, world, host_clips):
                 cur.wait_event(slot["ready"])
                 batch = {"frame_prev": keys_dev[kp], "frame_next": keys_dev[kn],
                          "mvs_left": _GridList(slot["gl"]), "mvs_right": _GridList(slot["gr"])}
-            labels = model.predict_step(batch, j)
+            with torch.no_grad():
+                labels = model.predict_step(batch, j)
             slot["free"].record(cur)
             key_free[kp].record(cur)              # prev is not needed after this interval (next stays for the following one)
             if it == n_int - 1:
@@ -529,12 +549,14 @@ def _GridList(stacked):
     return [stacked[j:j + 1] for j in range(stacked.shape[0])]
 
 
-def time_h2d_peak(mode, steps, clips_per_step, device, world, host_clips):
+def time_h2d_peak(mode, steps, clips_per_step, device, world, host_clips, inputs="logits"):
     """The e2e arm's own roofline: the SAME host buffers copied to the device with one plain pinned cudaMemcpyAsync
     per buffer (Tensor.copy_(non_blocking=True) of a pinned tensor), same order, no kernels, at the same N (all ranks
     copy at once: they share the host's memory system and PCIe root) -> (GB/s per GPU, bytes per step)."""
     n_int = (CLIP_FRAMES - 1) // K_DELTA
-    key_dev = [torch.empty((1, C, H, W), device=device) for _ in range(2)]
+    KC = 3 if inputs == "image" else C
+    key_bytes = KC * H * W * 4
+    key_dev = [torch.empty((1, KC, H, W), device=device) for _ in range(2)]
     gdev = None
     if mode != "linear":
         gshape = host_clips[0][1][0][0].shape
@@ -548,9 +570,9 @@ def time_h2d_peak(mode, steps, clips_per_step, device, world, host_clips):
             for it in range(n_int):
                 if it == 0:
                     key_dev[0].copy_(keys[0], non_blocking=True)
-                    nbytes += S_BYTES
+                    nbytes += key_bytes
                 key_dev[(it + 1) % 2].copy_(keys[it + 1], non_blocking=True)
-                nbytes += S_BYTES
+                nbytes += key_bytes
                 if gdev is not None:
                     gdev[0].copy_(grids[it][0], non_blocking=True)
                     gdev[1].copy_(grids[it][1], non_blocking=True)
@@ -895,19 +917,32 @@ def main():
     if not args.no_e2e:
         host_clips = [to_host_clip(c) for c in clips[:2]]
         e_steps = max(min(args.steps // 10, 20), 3)
-        ems, h2d, d2h, res = time_e2e(mode, e_steps, 3, args.clips_per_step, device, world, host_clips)
         e_frames = e_steps * args.clips_per_step * 3 * (K_DELTA - 1)
-        pk_gbs, pk_bytes = time_h2d_peak(mode, 3, args.clips_per_step, device, world, host_clips)
-        e_gbs = h2d / (ems / e_steps / 1e3) / 1e9
-        out["e2e"] = {"value": e_frames * world / (ems / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
-                      "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": ems / e_steps,
-                      "api": "FlowBaseModel.predict_step (pinned host key-frame logits + grids -> uint8 labels on host)",
-                      "temporal_miou": float(res.get("predict_miou1_epoch", float("nan"))),
-                      # the arm is bound by the host-to-device copies: its roofline is the rate of plain pinned copies
-                      # of the same buffers at the same number of ranks (per GPU)
-                      "pcie_gbs": e_gbs, "pcie_peak_gbs": pk_gbs, "frac": e_gbs / pk_gbs if pk_gbs > 0 else None,
-                      "pcie_peak_sample": f"3 steps of the same {pk_bytes} B per step, one pinned cudaMemcpyAsync per buffer, "
-                                          f"all {world} rank(s) at once"}
+
+        def e2e_arm(inputs, hclips, api):
+            ems, h2d, d2h, res = time_e2e(mode, e_steps, 3, args.clips_per_step, device, world, hclips, inputs)
+            pk_gbs, pk_bytes = time_h2d_peak(mode, 3, args.clips_per_step, device, world, hclips, inputs)
+            e_gbs = h2d / (ems / e_steps / 1e3) / 1e9
+            return {"value": e_frames * world / (ems / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e_steps, "ms_per_step": ems / e_steps, "api": api,
+                    "temporal_miou": float(res.get("predict_miou1_epoch", float("nan"))),
+                    # the arm is bound by the host-to-device copies: its roofline is the rate of plain pinned copies
+                    # of the same buffers at the same number of ranks (per GPU)
+                    "pcie_gbs": e_gbs, "pcie_peak_gbs": pk_gbs, "frac": e_gbs / pk_gbs if pk_gbs > 0 else None,
+                    "pcie_peak_sample": f"3 steps of the same {pk_bytes} B per step, one pinned cudaMemcpyAsync per buffer, "
+                                        f"all {world} rank(s) at once"}
+
+        # the reference's batches carry RGB frames (flow/dataset.py): [1,3,H,W] fp32 per key frame, the network output is at
+        # 1/8 of the frame and the interval entries take it from there
+        gen = torch.Generator().manual_seed(77 + rank)
+        img_clips = [([torch.randn((1, 3, H, W), generator=gen).pin_memory() for _ in hk], hg) for hk, hg in host_clips]
+        out["e2e"] = e2e_arm("image", img_clips,
+                             "FlowBaseModel.predict_step (pinned host RGB key frames [1,3,H,W] + grids -> stride-8 stand-in "
+                             "network on the GPU -> interval entry with decoder-resolution key frames -> uint8 labels on host)")
+        del img_clips
+        # r01's arm for continuity: full-resolution key-frame LOGITS uploaded, identity network
+        out["e2e_logits"] = e2e_arm("logits", host_clips,
+                                    "FlowBaseModel.predict_step (pinned host key-frame logits [1,C,H,W] + grids -> uint8 labels on host)")
     del clips
     torch.cuda.empty_cache()
 
