@@ -225,9 +225,11 @@ def test_deeplabv3_keyframes(cuda, feature_based, mode):
     assert torch.equal(kernels.argmax(got).long(), ref.max(1)[1])
 
 
-def test_keyframe_reuse_gives_identical_labels(cuda):
+@pytest.mark.parametrize("kind", ["block", "dense"])
+def test_keyframe_reuse_gives_identical_labels(cuda, kind):
     """Caching the `next` key frame's logits for the following interval halves the backbone
-    calls and must not change a single label or count."""
+    calls and must not change a single label or count.  On the dense route the cached decoder output is the very tensor
+    the next interval passes as `prev`, so its up-sample (kernels.KeyFrameUps) is reused as well."""
     H, W, n, C = 96, 128, 5, 5
     bb = TinyBackbone(classes=C).to(cuda).eval()
     calls = {"n": 0}
@@ -242,10 +244,12 @@ def test_keyframe_reuse_gives_identical_labels(cuda):
         calls["n"] = 0
         outs = []
         for it in range(3):
-            gl = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=9, interval=it, side=0)]
-            gr = [x.to(cuda) for x in flow_grids(H, W, n, "block", clip=9, interval=it, side=1)]
+            gl = [x.to(cuda) for x in flow_grids(H, W, n, kind, clip=9, interval=it, side=0)]
+            gr = [x.to(cuda) for x in flow_grids(H, W, n, kind, clip=9, interval=it, side=1)]
             outs.append(m.predict_step({"frame_prev": keys[it], "frame_next": keys[it + 1], "mvs_left": gl,
                                         "mvs_right": gr, "frame_id": torch.tensor([it * n])}, it).clone())
+            if kind == "dense" and reuse and it > 0:      # this interval's prev was found in the up-sample buffers
+                assert all(t is not None for t in m.model_G._dense_ups.tags)
         m.on_predict_end()
         results[reuse] = (outs, m.intersection_meter_predict.sum.copy(), calls["n"])
     assert results[False][2] == 6 and results[True][2] == 4
