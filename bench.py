@@ -853,6 +853,7 @@ def main():
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     kernels.load()
+    fuvs_comm = fdist.init_fuvs_comm()       # the counts' all-reduce goes through the C ABI (its own NCCL communicator)
 
     clips = [make_clip(mode, device, 1000 * rank + i) for i in range(args.distinct_clips)]
     sampler = ClockSampler(local)
@@ -887,6 +888,8 @@ def main():
     if world > 1:
         ok, detail = allreduce_parity(kernels, fdist, mode, rank, world, device)
         out["allreduce_parity"] = ok
+        out["collective"] = ("fuvs_allreduce_counts (NCCL all-reduce of the int64 counts behind the C ABI)" if fuvs_comm
+                             else "torch.distributed.all_reduce")
         if detail:
             out["allreduce_parity_detail"] = detail
 

@@ -32,6 +32,11 @@ SIGNATURES = {
     "fuvs_abi_version": (_i, []),
     "fuvs_last_error": (C.c_char_p, []),
     "fuvs_launch_count": (_ll, []),
+    "fuvs_comm_unique_id": (_i, [_p]),
+    "fuvs_comm_init": (_i, [_p, _i, _i]),
+    "fuvs_comm_world_size": (_i, []),
+    "fuvs_allreduce_counts": (_i, [_p, _ll, _p]),
+    "fuvs_comm_destroy": (_i, []),
     "fuvs_device_ok": (_i, []),
     "fuvs_linear_blend_argmax": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p]),
     "fuvs_linear_lowres_supported": (_i, [_i, _i, _i]),

@@ -111,8 +111,9 @@ class DeviceMeter:
         if getattr(self, "_reduced", False):
             return self
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from ..dist import allreduce_counts
             buf = torch.cat([self.counts.reshape(-1), torch.tensor([self.updates], dtype=torch.int64, device=self.device)])
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            allreduce_counts(buf)              # fuvs_allreduce_counts once dist.init_fuvs_comm() has run, else torch.distributed
             self.counts.copy_(buf[:-1].reshape(self.counts.shape))
             self.updates = int(buf[-1].item())
         self._reduced = True

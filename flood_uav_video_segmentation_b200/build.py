@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libfuvs.so")
-SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "dense_strip.cu", "block.cu", "block_rows.cu", "pointwise.cu", "feature.cu", "crop.cu", "metric.cu", "calib.cu"]
+SOURCES = ["abi.cu", "linear.cu", "warp.cu", "dense_tma.cu", "dense_strip.cu", "block.cu", "block_rows.cu", "pointwise.cu", "feature.cu", "crop.cu", "metric.cu", "calib.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
@@ -73,7 +73,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

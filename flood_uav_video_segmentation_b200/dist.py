@@ -67,8 +67,46 @@ def exchange_halo(last_label, rank, world, shape=None, device=None):
     return recv
 
 
+def init_fuvs_comm():
+    """Gives libfuvs its own NCCL communicator over the ranks of the initialised process group (one process per GPU):
+    rank 0 draws the ncclUniqueId through the C ABI, torch.distributed carries its 128 bytes to the other ranks, every
+    rank joins with fuvs_comm_init on its current device.  Returns True when `allreduce_counts` will go through
+    fuvs_allreduce_counts, False for a single process or a CPU (gloo) group."""
+    import ctypes
+
+    from ._lib import check, load
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2 or not torch.cuda.is_available():
+        return False
+    lib = load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if lib.fuvs_comm_world_size() == world:
+        return True
+    buf = (ctypes.c_ubyte * 128)()
+    if rank == 0:
+        check(lib.fuvs_comm_unique_id(buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    raw = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+    check(lib.fuvs_comm_init(raw, rank, world))
+    # NCCL connects lazily: the first collective of a fresh communicator sets the channels up (hundreds of ms)
+    from ._lib import ptr, stream_ptr
+    warm = torch.zeros(8, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    check(lib.fuvs_allreduce_counts(ptr(warm), warm.numel(), stream_ptr(warm.device)))
+    torch.cuda.synchronize()
+    return True
+
+
 def allreduce_counts(counts):
-    """The path's only collective: sum of the int64 [3,K] (or [M,3,K]) count buffers over all ranks, in place."""
+    """The path's only collective: sum of the int64 [3,K] (or [M,3,K]) count buffers over all ranks, in place —
+    fuvs_allreduce_counts (NCCL behind the C ABI) once `init_fuvs_comm` has run, torch.distributed otherwise."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if counts.is_cuda and counts.dtype == torch.int64 and counts.is_contiguous():
+            from ._lib import check, load, ptr, stream_ptr
+            lib = load()
+            if lib.fuvs_comm_world_size() == dist.get_world_size():
+                with torch.cuda.device(counts.device):
+                    check(lib.fuvs_allreduce_counts(ptr(counts), counts.numel(), stream_ptr(counts.device)))
+                return counts
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts

@@ -339,6 +339,22 @@ FUVS_API int fuvs_temporal_counts(const uint8_t* labels, int n, long long HW,
                          long long* counts, fuvs_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * The path's only collective: sum of the int64 count buffers over the ranks that shard the clips — one
+ * process per GPU, one NCCL all-reduce per evaluation.  The reference has no counterpart (it averages per-rank mIoU
+ * scalars, base/foundation.py:166-168); summing the integer (I,U,T) counts of util/util.py:36-63 reproduces the
+ * single-process result exactly.  NCCL is resolved at run time from the libnccl.so.2 the host process has loaded.
+ *   fuvs_comm_unique_id  : rank 0 fills 128 bytes (ncclUniqueId) that the host hands to every rank by its own means
+ *   fuvs_comm_init       : every rank, on its own device: joins the communicator (collective call)
+ *   fuvs_allreduce_counts: in-place sum of n int64 values (e.g. 3*K) on `stream`; counts is a device pointer
+ *   fuvs_comm_world_size : ranks of the communicator, 0 without one;  fuvs_comm_destroy: releases it
+ * ------------------------------------------------------------------------- */
+FUVS_API int fuvs_comm_unique_id(void* id128);
+FUVS_API int fuvs_comm_init(const void* id128, int rank, int world_size);
+FUVS_API int fuvs_comm_world_size(void);
+FUVS_API int fuvs_allreduce_counts(long long* counts, long long n, fuvs_stream_t stream);
+FUVS_API int fuvs_comm_destroy(void);
+
+/* ---------------------------------------------------------------------------
  * Sliding-crop inference (model.no_cropping=False) — flow/base.py:182-234.
  *
  * fuvs_crop_grid: crop_motion_vector for one grid (flow/transform.py:215-261,

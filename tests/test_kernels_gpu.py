@@ -738,3 +738,33 @@ def test_dense_lowres_interval(cuda, C, hl, wl, H, W, n):
         ref = fo.argmax_labels(fo.predict_segmentation(ident, ident, up(keys_lr[2]), up(keys_lr[0]), gl, gr, n, no_warp=False))
         labels, none = kernels.dense_lowres_interval(keys_lr[2], keys_lr[0], (H, W), gl, gr, n, ups=ups, scratch=scratch)
         assert none is None and torch.equal(labels.long().reshape(-1), ref.reshape(-1))
+
+
+def test_comm_single_rank_roundtrip(cuda):
+    """fuvs_comm_* / fuvs_allreduce_counts with a one-rank communicator (the multi-rank sum is checked on hardware by
+    bench.py --gpus N: `allreduce_parity`): unique id, init, an all-reduce that must leave the counts unchanged, destroy;
+    without a communicator the entry refuses loudly."""
+    import ctypes
+
+    from flood_uav_video_segmentation_b200._lib import FuvsError, check, load, ptr, stream_ptr
+    lib = load()
+    counts = torch.arange(15, dtype=torch.int64, device=cuda).reshape(3, 5) * 1000003
+    with pytest.raises(FuvsError):
+        check(lib.fuvs_allreduce_counts(ptr(counts), counts.numel(), stream_ptr(cuda)))
+    assert lib.fuvs_comm_world_size() == 0
+    buf = (ctypes.c_ubyte * 128)()
+    check(lib.fuvs_comm_unique_id(buf))
+    assert any(buf)
+    with torch.cuda.device(cuda):
+        check(lib.fuvs_comm_init(buf, 0, 1))
+        try:
+            assert lib.fuvs_comm_world_size() == 1
+            with pytest.raises(FuvsError):
+                check(lib.fuvs_comm_init(buf, 0, 1))                      # one communicator per process
+            before = counts.clone()
+            check(lib.fuvs_allreduce_counts(ptr(counts), counts.numel(), stream_ptr(cuda)))
+            torch.cuda.synchronize()
+            assert torch.equal(counts, before)
+        finally:
+            check(lib.fuvs_comm_destroy())
+    assert lib.fuvs_comm_world_size() == 0
