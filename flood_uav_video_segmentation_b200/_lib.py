@@ -16,7 +16,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfuvs.so")
 
-FUVS_ABI_VERSION = 2
+FUVS_ABI_VERSION = 3
 FUVS_BINS_HISTC = 0
 FUVS_BINS_NPHIST = 1
 FUVS_MUTATE_PRED = 2

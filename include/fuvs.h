@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define FUVS_ABI_VERSION 2
+#define FUVS_ABI_VERSION 3   /* 3: + fuvs_dense_lowres_interval_ptrs, fuvs_comm_*, fuvs_allreduce_counts (additive) */
 
 /* error codes */
 #define FUVS_OK        0
