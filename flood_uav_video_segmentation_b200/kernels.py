@@ -196,8 +196,13 @@ class KeyFrameUps:
 
 
 def _keyframe_tag(t, size, n, outputs):
-    # the tensor OBJECT (kept alive, so its storage cannot be handed to another tensor) and its version counter
-    return (t, t._version, tuple(size), n, outputs)
+    # the tensor OBJECT (kept alive, so its storage cannot be handed to another tensor) and its version counter;
+    # inference tensors (torch.inference_mode, Lightning's predict loop) do not track one: identity alone then
+    try:
+        version = t._version
+    except RuntimeError:
+        version = -1
+    return (t, version, tuple(size), n, outputs)
 
 
 def _same_tag(a, b):

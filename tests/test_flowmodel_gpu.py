@@ -237,13 +237,16 @@ def test_keyframe_reuse_gives_identical_labels(cuda, kind):
     g = torch.Generator().manual_seed(8)
     keys = [torch.randn(1, 3, H, W, generator=g).to(cuda) for _ in range(4)]
     results = {}
-    for reuse in (False, True):
+    for reuse in (False, True, "inference_mode"):
         m = FlowBaseModel(classes=C, arch="pspnet", feature_based=False, no_warp=False, no_cropping=True, backbone=bb,
-                          output_size=(H, W), reuse_keyframes=reuse).to(cuda).eval()
+                          output_size=(H, W), reuse_keyframes=bool(reuse)).to(cuda).eval()
         m.on_predict_start()
         calls["n"] = 0
         outs = []
-        for it in range(3):
+        # Lightning's predict loop runs under torch.inference_mode: its tensors carry no version counter
+        ctx = torch.inference_mode() if reuse == "inference_mode" else torch.no_grad()
+        with ctx:
+          for it in range(3):
             gl = [x.to(cuda) for x in flow_grids(H, W, n, kind, clip=9, interval=it, side=0)]
             gr = [x.to(cuda) for x in flow_grids(H, W, n, kind, clip=9, interval=it, side=1)]
             outs.append(m.predict_step({"frame_prev": keys[it], "frame_next": keys[it + 1], "mvs_left": gl,
@@ -252,10 +255,11 @@ def test_keyframe_reuse_gives_identical_labels(cuda, kind):
                 assert all(t is not None for t in m.model_G._dense_ups.tags)
         m.on_predict_end()
         results[reuse] = (outs, m.intersection_meter_predict.sum.copy(), calls["n"])
-    assert results[False][2] == 6 and results[True][2] == 4
-    for a, b in zip(results[False][0], results[True][0]):
-        assert torch.equal(a, b)
-    assert np.array_equal(results[False][1], results[True][1])
+    assert results[False][2] == 6 and results[True][2] == 4 and results["inference_mode"][2] == 4
+    for other in (True, "inference_mode"):
+        for a, b in zip(results[False][0], results[other][0]):
+            assert torch.equal(a, b)
+        assert np.array_equal(results[False][1], results[other][1])
 
 
 def test_keyframe_cache_is_invalidated_by_weight_and_mode_changes(cuda):
