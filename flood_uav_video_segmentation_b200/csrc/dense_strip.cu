@@ -52,6 +52,16 @@
 #include "dense_common.cuh"
 #include "tma_ptx.cuh"
 
+// Developer build -DFUVS_STRIP_ASSERT (tools/strip_asserts.sh): bounds checks of every ring address, global index,
+// slot number and completion-counter value of the barrier-free protocol — compute-sanitizer is closed on the GPU pool
+// this was developed on (profiles/r02_sanitizer_unavailable.txt), so the kernel checks itself under the parity tests.
+#ifdef FUVS_STRIP_ASSERT
+#include <cassert>
+#define STRIP_ASSERT(x) assert(x)
+#else
+#define STRIP_ASSERT(x) ((void)0)
+#endif
+
 namespace fuvs {
 
 namespace {
@@ -301,6 +311,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
       const bool side = u >= G.nsx;
       const int strip = side ? u - G.nsx : u;
       const int b = s % NS;
+      STRIP_ASSERT(s >= 0 && b >= 0 && b < NS && NS <= MAX_SLOTS && u < 2 * G.nsx && strip < G.nsx);
       const uint32_t bar = bar0 + 8u * b;
       if (ytop + RB <= 0 || ytop >= H) {
         mbar_arrive(bar);                    // slot entirely outside the image: never read (border clipping)
@@ -411,6 +422,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         const int y0 = (j0 + jj) * RB;
         const int wy0 = y0 - HALO_Y;
         const int pix0 = (y0 + ty) * W + x;
+        STRIP_ASSERT(y0 >= 0 && y0 < H + RB && (j0 + jj) < G.nby);
         const int ky = -0x4B000000 - wy0;            // window row of a tap: mantissa bits of (iy + 2^23) + ky
         const int rb0 = b0 * RB;                     // ring row of the window's top row
 
@@ -448,9 +460,13 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
           // ring element (row, column) of the north-west tap and of the one below it; byte addresses are formed at
           // the loads (x4 planar, x16 and x4 for the two parts of a 4+1 window)
           const unsigned e = rr * BOXW + lx;
+          STRIP_ASSERT(!in_box || (rr < static_cast<unsigned>(NSR) && lx < static_cast<unsigned>(BOXW)));
           aN[r] = in_box ? e : 0u;
           aS[r] = in_box ? ((rr == static_cast<unsigned>(NSR - 1)) ? e - static_cast<unsigned>((NSR - 1) * BOXW) : e + BOXW)
                          : 0u;
+          STRIP_ASSERT(aN[r] < static_cast<unsigned>(NSR * BOXW) && aS[r] < static_cast<unsigned>(NSR * BOXW));
+          // the east tap may sit one element further (pad / next region), never beyond the 64 bytes behind the ring
+          STRIP_ASSERT(pdx[r] ? (aN[r] % BOXW) + 1u < static_cast<unsigned>(BOXW) || !in_box : true);
         }
         // ---- this set's flow vectors are consumed: refill it for block jj + 2 (nothing here depends on the ring)
         load_grid(y0 + 2 * RB, jj + 2 < nb, g);
@@ -613,6 +629,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
           for (int r = 0; r < PX; ++r) {
             if (!live[r]) continue;
             const int pix = pix0 + r * rstride;
+            STRIP_ASSERT(pix >= 0 && pix < HWi && am[r].idx >= 0 && am[r].idx < C);
             if (EMIT && lab_out) lab_out[pix] = static_cast<uint8_t>(am[r].idx);
             if (KEY0 && do_key0 && A.label0) A.label0[pix] = static_cast<uint8_t>(am[r].idx);
           }
@@ -626,7 +643,11 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         tok_to = (jj < nb - 1) ? sb + jj + 1 : sb + nb + WIN - 1;
         released = tok_to;
         tok_want = (static_cast<unsigned>(kglob >> 2) + 1u) * NWARPS - 1u;
-        if (lane == 0) tok = atom_add_relaxed(done0 + 4u * (kglob & 3), 1u);
+        if (lane == 0) {
+          tok = atom_add_relaxed(done0 + 4u * (kglob & 3), 1u);
+          // visits of a counter never mix: the old value lies inside this visit's window of NWARPS arrivals
+          STRIP_ASSERT(tok >= static_cast<unsigned>(kglob >> 2) * NWARPS && tok <= tok_want);
+        }
         ++kglob;
         if (++b0 == NS) { b0 = 0; q0 ^= 1u; }
       }

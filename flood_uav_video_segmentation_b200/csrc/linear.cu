@@ -494,10 +494,9 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
-      if (atomicAdd(&done[s * BULK_NQ + q], 1u) == BULK_QWARPS - 1) {
-        done[s * BULK_NQ + q] = 0u;
-        issue(i + BULK_STAGES);
-      }
+      // the counter only grows (no reset to race with): visit v = i / STAGES of a stage is complete at (v + 1) * QWARPS
+      const unsigned last = (static_cast<unsigned>(i / BULK_STAGES) + 1u) * BULK_QWARPS - 1u;
+      if (atomicAdd(&done[s * BULK_NQ + q], 1u) == last) issue(i + BULK_STAGES);
     }
     if (live) {
       u64 probe = zero2;
