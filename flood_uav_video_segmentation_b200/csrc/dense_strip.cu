@@ -61,6 +61,23 @@
 #else
 #define STRIP_ASSERT(x) ((void)0)
 #endif
+// -DFUVS_STRIP_JITTER: every warp stalls for a pseudo-random 0 .. 16 k cycles at a pseudo-random third of its blocks
+// (before it reads the ring and before it hands a block back), so that the warps of a CTA drift apart as far as the
+// protocol lets them and the hand-over runs under every interleaving the parity tests can provoke.
+#ifdef FUVS_STRIP_JITTER
+#define STRIP_JITTER(salt)                                                                              \
+  do {                                                                                                  \
+    unsigned h_ = (static_cast<unsigned>(kglob) * 2654435761u) ^ ((threadIdx.x >> 5) * 40503u) ^        \
+                  (blockIdx.x * 2246822519u) ^ (salt);                                                  \
+    h_ ^= h_ >> 15; h_ *= 2246822519u; h_ ^= h_ >> 13;                                                  \
+    if ((h_ % 3u) == 0u) {                                                                              \
+      const long long t_ = clock64() + ((h_ >> 8) & 16383u);                                            \
+      while (clock64() < t_) {}                                                                         \
+    }                                                                                                   \
+  } while (0)
+#else
+#define STRIP_JITTER(salt) ((void)0)
+#endif
 
 namespace fuvs {
 
@@ -473,6 +490,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         const bool use_global = __any_sync(0xffffffffu, outside);
         refill_if_last();
 
+        STRIP_JITTER(0x9e3779b9u);
         // ---- the ring slots of this block's window: the newest one, and all of them at the start of a segment
         if (jj == 0) {
 #pragma unroll
@@ -638,6 +656,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
         // ---- this warp is done with the ring for block kglob (its gathers have returned: the FMAs consumed them).
         // done[kglob & 3] only grows: visit v = kglob >> 2 of a counter is complete at (v + 1) * NWARPS; the skew
         // between warps is bounded by the prefetch depth (< 4 blocks), so visits never mix.
+        STRIP_JITTER(0x85ebca6bu);
         __syncwarp();
         tok_from = released;
         tok_to = (jj < nb - 1) ? sb + jj + 1 : sb + nb + WIN - 1;
