@@ -13,6 +13,29 @@
 #include "fuvs_common.cuh"
 #include "pix4.cuh"
 
+// Developer build -DFUVS_STRIP_ASSERT / -DFUVS_STRIP_JITTER (tools/strip_asserts.sh, see dense_strip.cu): the bulk kernel's
+// barrier-free stage hand-over checks its counters and indices itself and runs with pseudo-random per-warp stalls.
+#ifdef FUVS_STRIP_ASSERT
+#include <cassert>
+#define LIN_ASSERT(x) assert(x)
+#else
+#define LIN_ASSERT(x) ((void)0)
+#endif
+#ifdef FUVS_STRIP_JITTER
+#define LIN_JITTER(i_, salt)                                                                            \
+  do {                                                                                                  \
+    unsigned h_ = (static_cast<unsigned>(i_) * 2654435761u) ^ ((threadIdx.x >> 5) * 40503u) ^           \
+                  (blockIdx.x * 2246822519u) ^ (salt);                                                  \
+    h_ ^= h_ >> 15; h_ *= 2246822519u; h_ ^= h_ >> 13;                                                  \
+    if ((h_ % 3u) == 0u) {                                                                              \
+      const long long t_ = clock64() + ((h_ >> 8) & 16383u);                                            \
+      while (clock64() < t_) {}                                                                         \
+    }                                                                                                   \
+  } while (0)
+#else
+#define LIN_JITTER(i_, salt) ((void)0)
+#endif
+
 namespace fuvs {
 
 template <int CT, int VEC, bool COUNTS>
@@ -457,6 +480,8 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
     if (t * BULK_TILE + q * BULK_QPX >= HW) break;              // this quarter of the last tile is past the end: no load was issued
     const LabelWord tc_next = tc_load(t + gridDim.x);
     const int s = static_cast<int>(i % BULK_STAGES);
+    LIN_JITTER(i, 0x9e3779b9u);
+    LIN_ASSERT(s >= 0 && s < BULK_STAGES && q >= 0 && q < BULK_NQ);
     lin_wait(lin_smem_u32(&bars[s * BULK_NQ + q]), static_cast<uint32_t>((i / BULK_STAGES) & 1));
     const float* sb = stage_base + static_cast<size_t>(s) * 2 * CT * BULK_TILE + tid * NPX;
     const long long pix = t * BULK_TILE + tid * NPX;
@@ -491,12 +516,16 @@ linear_blend_argmax_bulk_kernel(const float* __restrict__ prev, const float* __r
       }
     }
     // operands are in registers: hand the slice back; the last warp of the quarter refills it with tile i + STAGES
+    LIN_JITTER(i, 0x85ebca6bu);
+    LIN_ASSERT(!live || (pix >= 0 && pix + NPX <= HW));
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
       // the counter only grows (no reset to race with): visit v = i / STAGES of a stage is complete at (v + 1) * QWARPS
       const unsigned last = (static_cast<unsigned>(i / BULK_STAGES) + 1u) * BULK_QWARPS - 1u;
-      if (atomicAdd(&done[s * BULK_NQ + q], 1u) == last) issue(i + BULK_STAGES);
+      const unsigned old = atomicAdd(&done[s * BULK_NQ + q], 1u);
+      LIN_ASSERT(old + BULK_QWARPS > last && old <= last);        // visits of a stage's counter never mix
+      if (old == last) issue(i + BULK_STAGES);
     }
     if (live) {
       u64 probe = zero2;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Self-checking run of the dense strip kernel (compute-sanitizer is closed on the pool): builds libfuvs with
+# Self-checking run of the dense strip kernel and the linear bulk kernel (compute-sanitizer is closed on the pool): builds libfuvs with
 # -DFUVS_STRIP_ASSERT (device-side assert() on every ring address, slot number, global index and completion-counter value)
 # and runs the dense parity tests and one bench-sized clip against it.  A failing assert aborts the process.
 set -e
@@ -13,14 +13,14 @@ from flood_uav_video_segmentation_b200 import _lib
 _lib.use_library(os.environ["FUVS_DEV_LIB"])
 import pytest
 rc = pytest.main(["tests/test_kernels_gpu.py", "tests/test_golden_gpu.py", "tests/test_flowmodel_gpu.py", "-q", "-m", "gpu", "-x",
-                  "-k", "dense or 1080p or golden or predict_matches or reuse", "-p", "no:cacheprovider"])
+                  "-k", "dense or linear or 1080p or golden or predict_matches or reuse", "-p", "no:cacheprovider"])
 print("pytest under -DFUVS_STRIP_ASSERT rc =", int(rc))
 import torch, bench
 from flood_uav_video_segmentation_b200 import kernels
 dev = torch.device("cuda", 0)
-for mode in ("dense", "dense_smooth", "dense_lowres"):
+for mode in ("dense", "dense_smooth", "dense_lowres", "linear"):
     clip = bench.make_clip(mode, dev, 3)
-    scratch = torch.empty((bench.scratch_floats(kernels, mode),), dtype=torch.float32, device=dev)
+    scratch = torch.empty((max(bench.scratch_floats(kernels, mode), 1),), dtype=torch.float32, device=dev)
     counts = kernels.new_counts(bench.C, dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     bench.run_clip(kernels, mode, clip, counts, scratch)
