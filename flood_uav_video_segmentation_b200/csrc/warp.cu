@@ -257,9 +257,7 @@ static int dense_interval_impl(const float* prev, const float* next, const float
     make_blend_weights(n, &w);
     // Step kernels, in order of preference: strip (sliding-window TMA kernel, dense_strip.cu), plane (per-plane TMA
     // kernel, dense_tma.cu: C > 6), direct (L1 gather, this file: W % 4 != 0, even-n middle step).  Shapes a kernel
-    // cannot take fall through to the next one.  C = 5 with odd n keeps its chain states in the strip kernel's 4+1
-    // layout; that is decided here, once, because a state written 4+1 must be read 4+1.
-    // (only when frames are emitted: step 1 is then the key-frame variant, the one that reads a planar source)
+    // cannot take fall through to the next one (`il`, decided above, excludes that for 4+1 intervals).
     float* Lst = scratch;                       // states 1..n-2
     float* Rst = scratch + (n > 2 ? (n - 2) * S : 0);
     for (int j = 1; j <= n - 1; ++j) {
