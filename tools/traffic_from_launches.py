@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = {}
 detail = {}
-for mode in ("dense", "dense_smooth", "block", "block_clip", "linear", "linear_lowres"):
+for mode in ("dense", "dense_smooth", "dense_lowres", "block", "block_clip", "block_lowres", "linear", "linear_lowres"):
     p = os.path.join(ROOT, "profiles", f"r02_launches_{mode}.csv")
     if not os.path.exists(p):
         continue
