@@ -543,6 +543,25 @@ def test_errors_are_loud(cuda):
         kernels.linear_blend_argmax(torch.zeros(5, 8, 8, device=cuda), torch.zeros(5, 8, 8, device=cuda), 500)
     with pytest.raises(kernels.FuvsError):
         kernels.confusion(torch.zeros(4, device=cuda), torch.zeros(4, dtype=torch.int64, device=cuda), 5)
+    # fuvs_dense_lowres_interval_ptrs: the two up-sample buffers must be distinct, the key frames and buffers non-NULL
+    from flood_uav_video_segmentation_b200._lib import check, load, ptr, ptr_array, stream_ptr
+    lib = load()
+    C, hl, wl, H, W, n = 5, 8, 16, 64, 128, 3
+    lr = torch.zeros(C, hl, wl, device=cuda)
+    up = torch.empty(C * H * W, device=cuda)
+    up2 = torch.empty(C * H * W, device=cuda)
+    grids = [torch.zeros(1, H, W, 2, device=cuda) for _ in range(n - 1)]
+    scratch = torch.empty(int(lib.fuvs_dense_scratch_floats(C, H, W, n)), device=cuda)
+    labels = torch.empty((n, H, W), dtype=torch.uint8, device=cuda)
+
+    def call(prev_lr, next_lr, prev_up, next_up):
+        check(lib.fuvs_dense_lowres_interval_ptrs(ptr(prev_lr), ptr(next_lr), hl, wl, ptr(prev_up), 0, ptr(next_up), ptr_array(grids),
+                                                  ptr_array(grids), C, H, W, n, ptr(scratch), ptr(labels), None, None, None, 255,
+                                                  stream_ptr(cuda)))
+    call(lr, lr, up, up2)                                   # the valid call
+    for bad in ((lr, lr, up, up), (None, lr, up, up2), (lr, None, up, up2), (lr, lr, None, up2), (lr, lr, up, None)):
+        with pytest.raises(kernels.FuvsError):
+            call(*bad)
 
 
 def test_limits_and_degenerate_shapes(cuda):
