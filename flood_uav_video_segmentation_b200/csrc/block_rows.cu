@@ -289,7 +289,10 @@ block_rows_kernel(const float* __restrict__ key0, const float* __restrict__ Lst,
             }
           }
           u64 idx0[2];
-          exact_scan(xp, idx0);
+          bool nan0 = false;                           // float-domain arg-max like frames 1..n-1, exact scan only for NaN
+          idx0[0] = argmax2f_nan<CT>(xp[0], &nan0);
+          idx0[1] = argmax2f_nan<CT>(xp[1], &nan0);
+          if (nan0) exact_scan(xp, idx0);
           // the slot's values are consumed (the scan above depends on them): the next row's key frame may land in it
           // (requesting it into registers during the last frame instead hides its latency and changes nothing: 49.1 us)
           if (!KLR && r + 1 < R) start_key(pix[r + 1]);
