@@ -759,6 +759,23 @@ def test_dense_lowres_interval(cuda, C, hl, wl, H, W, n):
         assert none is None and torch.equal(labels.long().reshape(-1), ref.reshape(-1))
 
 
+@pytest.mark.parametrize("jitter", [0.3, 1.5])
+def test_dense_lowres_interval_large_motion(cuda, jitter):
+    """Decoder-resolution key frames with taps far outside the strip kernel's window (and outside the image): step 1's
+    warps then gather from the 4+1 key frames in global memory (block_from_global with both layouts 4+1)."""
+    C, hl, wl, H, W, n = 5, 34, 64, 272, 512, 5
+    g = torch.Generator().manual_seed(31)
+    o_lr, o_next_lr = ((torch.randn(1, C, hl, wl, generator=g) * 3).to(cuda) for _ in range(2))
+    up = lambda t: F.interpolate(t, size=(H, W), mode="bilinear", align_corners=True)      # noqa: E731
+    gl = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=12, side=0, jitter=jitter)]
+    gr = [x.to(cuda) for x in flow_grids(H, W, n, "dense", clip=12, side=1, jitter=jitter)]
+    ref_logits = fo.predict_segmentation(ident, ident, up(o_lr), up(o_next_lr), gl, gr, n, no_warp=False)
+    labels, logits = kernels.dense_lowres_interval(o_lr, o_next_lr, (H, W), gl, gr, n, want_labels=True, want_logits=True)
+    bad = int((logits.reshape(-1).view(torch.int32) != ref_logits.reshape(-1).view(torch.int32)).sum())
+    assert bad == 0, f"{bad} logits differ from F.interpolate + the reference sequence"
+    assert torch.equal(labels.long().reshape(-1), fo.argmax_labels(ref_logits).reshape(-1))
+
+
 def test_comm_single_rank_roundtrip(cuda):
     """fuvs_comm_* / fuvs_allreduce_counts with a one-rank communicator (the multi-rank sum is checked on hardware by
     bench.py --gpus N: `allreduce_parity`): unique id, init, an all-reduce that must leave the counts unchanged, destroy;
