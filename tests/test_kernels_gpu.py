@@ -776,6 +776,29 @@ def test_dense_lowres_interval_large_motion(cuda, jitter):
     assert torch.equal(labels.long().reshape(-1), fo.argmax_labels(ref_logits).reshape(-1))
 
 
+@pytest.mark.parametrize("C,H,W,n", [(5, 272, 512, 5), (5, 96, 132, 3), (2, 64, 128, 4)])
+def test_dense_interval_nan_and_inf(cuda, C, H, W, n):
+    """Key frames with NaN, +Inf and -Inf class values through the dense route (strip kernel with 4+1 and planar states,
+    the direct kernel for the even-n middle step): taps with weight zero at the border must not pull a NaN in, a NaN
+    class value wins the arg-max like in torch.max, Inf - Inf in a blend makes a NaN on the way."""
+    o, o_next = keyframe_logits(C, H, W, 8, 0)[None], keyframe_logits(C, H, W, 8, 1)[None]
+    for k, (t, v) in enumerate(((o, float("nan")), (o_next, float("inf")), (o, float("-inf")), (o_next, float("nan")),
+                                (o, float("inf")), (o_next, float("-inf")))):
+        t[0, k % C, (2 * k + 1)::7, (3 * k)::5] = v
+    o[0, :, 0, :] = float("inf")                # image border rows / columns: the clipped taps
+    o_next[0, :, :, W - 1] = float("nan")
+    gl = [g.to(cuda) for g in flow_grids(H, W, n, "dense", clip=8, side=0, jitter=0.05)]
+    gr = [g.to(cuda) for g in flow_grids(H, W, n, "dense", clip=8, side=1, jitter=0.05)]
+    oc, onc = o.to(cuda), o_next.to(cuda)
+    ref_logits = fo.predict_segmentation(ident, ident, oc, onc, gl, gr, n, False)
+    labels, logits = kernels.dense_interval(oc, onc, gl, gr, n, want_labels=True, want_logits=True)
+    assert bool(torch.isnan(ref_logits).any()) and bool(torch.isinf(ref_logits).any())
+    a, b = logits.reshape(-1), ref_logits.reshape(-1)
+    bad = int(((a.view(torch.int32) != b.view(torch.int32)) & ~(torch.isnan(a) & torch.isnan(b))).sum())     # any NaN equals any NaN
+    assert bad == 0, f"{bad} logits differ from torch-CUDA oracle"
+    assert torch.equal(labels.long().reshape(-1), fo.argmax_labels(ref_logits).reshape(-1))
+
+
 def test_comm_single_rank_roundtrip(cuda):
     """fuvs_comm_* / fuvs_allreduce_counts with a one-rank communicator (the multi-rank sum is checked on hardware by
     bench.py --gpus N: `allreduce_parity`): unique id, init, an all-reduce that must leave the counts unchanged, destroy;
