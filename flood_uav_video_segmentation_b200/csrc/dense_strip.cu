@@ -50,6 +50,7 @@
 #include <utility>
 
 #include "dense_common.cuh"
+#include "pix4.cuh"
 #include "tma_ptx.cuh"
 
 // Developer build -DFUVS_STRIP_ASSERT (tools/strip_asserts.sh): bounds checks of every ring address, global index,
@@ -191,6 +192,32 @@ __device__ __forceinline__ unsigned atom_add_relaxed(uint32_t addr, unsigned v) 
   unsigned old;
   asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
+}
+
+// First maximum over CT class values with torch.max's rules (lowest index wins ties, the first NaN wins outright): the
+// class maxima propagate NaN (max.NaN), the index is the number of leading classes that differ from the maximum (pix4.cuh);
+// a pixel with a NaN class value takes the compare-select scan.  10 instead of 20 instructions per pixel.
+template <int CT>
+__device__ __forceinline__ int argmax_classes(const float (&v)[CT]) {
+  if constexpr (CT < 2) {
+    return 0;
+  } else {
+    const float m = max_classes_nan<CT>(v);
+    if (m != m) {
+      ArgMax am;
+      am.init(-INFINITY);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) am.push(v[c], c);
+      return am.idx;
+    }
+    float t = differs(v[CT - 2], m);
+#pragma unroll
+    for (int c = CT - 3; c >= 0; --c) {
+      const float nc = differs(v[c], m);
+      t = __fmaf_rn(nc, t, nc);
+    }
+    return __float2int_rz(t);
+  }
 }
 
 // Element (channel c, pixel off) of a state: planar [C][HW], or 4+1 (channels 0-3 interleaved, channel 4 a plane).
@@ -584,6 +611,7 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
             for (int r = 0; r < PX; ++r) {
               const bool dxy = pdx[r] && pdy[r];
               float accs[CT];
+              float vals[CT];                           // the frame's class values of this pixel (EMIT / frame 0)
 #pragma unroll
               for (int c = 0; c < CT; ++c) {
                 const int gi = c * HWi + pix0 + r * rstride;
@@ -597,14 +625,15 @@ dense_strip_kernel(const __grid_constant__ StripMaps M, const __grid_constant__ 
                   // fl(fl(w_this*acc) + fl(w_point*o)): IEEE addition is commutative, so one operand order serves both
                   // sides (the reference adds the forward term first on both) and the code is not duplicated per side
                   const float val = blend2(w_this, acc, w_point, other[r][c]);
-                  am[r].push(val, c);
+                  vals[c] = val;
                   if (w_lp && live[r]) __stcs(logit_out + gi, val);
                 }
                 if (KEY0 && do_key0) {
-                  am[r].push(vk[r][c], c);
+                  vals[c] = vk[r][c];
                   if (w_l0 && live[r]) __stcs(A.logit0 + gi, vk[r][c]);
                 }
               }
+              if (EMIT || (KEY0 && do_key0)) am[r].idx = argmax_classes<CT>(vals);
               if constexpr (IL) {
                 if (w_dst && live[r]) {
                   const int pix = pix0 + r * rstride;
