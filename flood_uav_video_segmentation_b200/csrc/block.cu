@@ -21,7 +21,8 @@ namespace fuvs {
 
 int launch_block_stream_rows(const float* key0, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
                              int n, float sh, float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev,
-                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl);
+                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl,
+                             bool* counts_done);
 int launch_temporal_counts(const uint8_t* labels, int n, long long HW, const uint8_t* tc_prev, int K,
                            int ignore_index, long long* counts, cudaStream_t st);
 int launch_argmax(const float* logits, int frames, int C, long long HW, uint8_t* u8, long long* i64, cudaStream_t st);
@@ -632,10 +633,9 @@ static int block_frames(const float* prev, const float* Lst, const float* Rst, i
   const float sh = ac_scale(Hg, H), sw = ac_scale(Wg, W);
   if (hl > 0) {      // key frame at decoder resolution: only the row kernel evaluates its up-sample on the fly
     const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts,
-                                           ignore_index, w, st, hl, wl);
+                                           ignore_index, w, st, hl, wl, counts_done);
     if (r < 0) return r;
     if (r > 0) return set_error(FUVS_EINVAL, "block_lowres: shape not supported (see fuvs_block_lowres_supported)");
-    *counts_done = counts != nullptr;
     return FUVS_OK;
   }
   if (Hg == H && Wg == W) {
@@ -651,12 +651,10 @@ static int block_frames(const float* prev, const float* Lst, const float* Rst, i
   }
   // source-row intervals (block_rows.cu) for the shapes it takes (2 <= C <= 5, W % 4 == 0), column strips otherwise
   const int r = launch_block_stream_rows(prev, Lst, Rst, C, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts,
-                                         ignore_index, w, st, 0, 0);
+                                         ignore_index, w, st, 0, 0, counts_done);
   if (r < 0) return r;
-  if (r == 0) {
-    *counts_done = counts != nullptr;
-    return FUVS_OK;
-  }
+  if (r == 0) return FUVS_OK;                   // (the row kernel says whether it took the counts)
+  *counts_done = false;
   dim3 grid((W + STHREADS - 1) / STHREADS, (H + SROWS - 1) / SROWS);
   if (grid.y > 65535) return set_error(FUVS_EINVAL, "block: H=%d too large", H);
   auto cu = reinterpret_cast<unsigned long long*>(counts);

@@ -350,7 +350,7 @@ static bool key_rows_fit(int H, int Hg, float sh, int hl, float shk) {
 template <int CT, bool KLR>
 int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int W, int Hg, int Wg, int n, float sh,
               float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev, long long* counts, int ignore_index,
-              const BlendWeights& w, cudaStream_t st, int hl, int wl, float shk, float swk) {
+              const BlendWeights& w, cudaStream_t st, int hl, int wl, float shk, float swk, bool* counts_done) {
   // shared memory: (n-1) frames x 2 states x 2 rows x CT channels x XW columns
   const long long per_col = 4ll * (n - 1) * CT * 4;
   const int budget = 108 * 1024 - BR_THREADS * CT * 16;   // two CTAs per SM, minus the key-frame staging slots
@@ -370,9 +370,11 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
   const bool spec = CT == 5 && XW == 256 && n == 5;
 #define FUVS_BR(CNT_, LG_)                                                                                             \
   do {                                                                                                                 \
-    auto kern = spec ? block_rows_kernel<CT, CNT_, LG_, KLR, (CT == 5)> : block_rows_kernel<CT, CNT_, LG_, KLR, false>;  \
+    /* (the labels-only low-res variant spills 584 bytes when specialised: it keeps the generic kernel) */              \
+    const bool sp = spec && !(KLR && !CNT_ && !LG_);                                                                   \
+    auto kern = sp ? block_rows_kernel<CT, CNT_, LG_, KLR, (CT == 5)> : block_rows_kernel<CT, CNT_, LG_, KLR, false>;    \
     static SmemOptIn optin[2];                     /* one per kernel: the opt-in is an attribute of the function */      \
-    if (!optin[spec ? 1 : 0].ensure(kern, 110 * 1024)) return 1;                                                       \
+    if (!optin[sp ? 1 : 0].ensure(kern, 110 * 1024)) return 1;                                                         \
     cudaLaunchConfig_t cfg = {};                                                                                       \
     cfg.gridDim = dim3(Hg * nchunks);                                                                                  \
     cfg.blockDim = dim3(BR_THREADS);                                                                                   \
@@ -387,8 +389,23 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
                                               labels, logits, tc_prev, cu, ignore_index, w, 1.0f, hl, wl, shk, swk);   \
     if (le != cudaSuccess) return set_error(FUVS_ECUDA, "fuvs_block_interval(stream rows): %s", cudaGetErrorString(le)); \
   } while (0)
-  if (counts) { if (logits) FUVS_BR(true, true); else FUVS_BR(true, false); }
-  else        { if (logits) FUVS_BR(false, true); else FUVS_BR(false, false); }
+  // The counts stay in the kernel only on the low-resolution route (37.8 us per 1080p interval against ~44 with the
+  // separate launch).  With full-resolution key frames they are 12 % of the kernel's instructions and the bit-plane
+  // fuvs_temporal_counts (4.3 us) does them cheaper: block 48.1 -> 47.3, clip entry 45.4 -> 42.0 us per interval.
+  *counts_done = false;
+  bool fused = false;
+  if constexpr (KLR) {
+    if (counts) {
+      if (logits) FUVS_BR(true, true); else FUVS_BR(true, false);
+      fused = true;
+      *counts_done = true;
+    }
+  }
+  if (!fused) {
+    cu = nullptr;
+    tc_prev = nullptr;
+    if (logits) FUVS_BR(false, true); else FUVS_BR(false, false);
+  }
 #undef FUVS_BR
   count_launch();
   return FUVS_OK;
@@ -396,12 +413,14 @@ int launch_ct(const float* key0, const float* Lst, const float* Rst, int H, int 
 
 }  // namespace
 
-// Returns FUVS_OK if it ran (labels, logits and — when counts != NULL — the temporal counts are done), 1 if the
+// Returns FUVS_OK if it ran (labels and logits are done; *counts_done says whether the temporal counts are too), 1 if the
 // shape is not eligible (the caller uses block_stream_cols_kernel), negative on error.
 // hl > 0: key0 is the key frame at decoder resolution [C,hl,wl] (frame 0 = arg-max of its up-sample).
 int launch_block_stream_rows(const float* key0, const float* Lst, const float* Rst, int C, int H, int W, int Hg, int Wg,
                              int n, float sh, float sw, uint8_t* labels, float* logits, const uint8_t* tc_prev,
-                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl) {
+                             long long* counts, int ignore_index, const BlendWeights& w, cudaStream_t st, int hl, int wl,
+                             bool* counts_done) {
+  *counts_done = false;
   if (C < 2 || C > 5 || (W & 3) != 0 || n < 2) return 1;
   const bool klr = hl > 0;
   if ((!klr && !aligned16(key0)) || (logits && !aligned16(logits)) || (labels && !aligned4(labels)) || (tc_prev && !aligned4(tc_prev)))
@@ -416,9 +435,9 @@ int launch_block_stream_rows(const float* key0, const float* Lst, const float* R
   }
 #define FUVS_BRC(CT_)                                                                                                  \
   return klr ? launch_ct<CT_, true>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, w, \
-                                    st, hl, wl, shk, swk)                                                               \
+                                    st, hl, wl, shk, swk, counts_done)                                                  \
              : launch_ct<CT_, false>(key0, Lst, Rst, H, W, Hg, Wg, n, sh, sw, labels, logits, tc_prev, counts, ignore_index, \
-                                     w, st, 0, 0, 0.f, 0.f)
+                                     w, st, 0, 0, 0.f, 0.f, counts_done)
   switch (C) {
     case 2: FUVS_BRC(2);
     case 3: FUVS_BRC(3);
