@@ -876,7 +876,7 @@ def main():
                         "traffic": measured_traffic(mode), "peak_source": peak_src, "kernel": f"fuvs_{mode}_interval",
                         "algorithmic_bytes_per_launch": bytes_iv, "us_per_launch": ms * 1e3 / intervals,
                         "launch": "one interval = one C-ABI call (dense: 4 dense_strip_kernel steps + 1 temporal_counts_v16_kernel; "
-                                  "block: chain + frame kernel; linear: one kernel); duration = CUDA events over the "
+                                  "block: chain steps + frame kernel + temporal_counts_v16_kernel (fused into the frame kernel on the low-res route); linear: one kernel); duration = CUDA events over the "
                                   "timed region / intervals",
                         "frac_of_nominal_8000": achieved / 8000.0},
            # content-dependent: the all-reduced temporal-consistency intersections (sum over classes)
